@@ -1,0 +1,434 @@
+"""Host-side mirror of the reference's entry points for the form-factor + gather path, over the C-ABI.
+
+Same names, argument meaning and (print-and-continue vs. raise aside) behaviour as the reference classes:
+
+* :class:`MeshS`                     -- ``visual studio/MeshS.h:7-26`` (patch layout + materials)
+* :class:`OptixPrimeFunctionality`   -- ``visual studio/OptixPrimeFunctionality.h:24-48``
+* :class:`Lightning` and its three flavours -- ``visual studio/Lightning.h``
+
+The heavy lifting is in ``libdaisy_b200.so`` (hand-written sm_100a kernels); nothing here computes on the CPU
+except O(N*K) input preparation and the colour cache.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import struct
+
+import numpy as np
+
+from . import _lib
+from . import materials as _mat
+from . import rgb2spec as _r2s
+from .scenes import RAYS_PER_PATCH, Scene, load_obj, msvc_sample_pattern
+
+HIT_DTYPE = _lib.HIT_DTYPE
+
+
+class MeshS:
+    """Reference ``MeshS``: public arrays ``vertices``, ``normals``, ``triangleIndices``, ``materials``,
+    ``materialIndexPerTriangle``, ``numtriangles`` (``MeshS.h:14-20``)."""
+
+    def __init__(self, filepath=None, mtlpath=None, wavelengths=None, coeff_table=None):
+        self.vertices = np.zeros((0, 3), np.float32)
+        self.normals = np.zeros((0, 3), np.float32)
+        self.triangleIndices = np.zeros((0, 6), np.int32)
+        self.materials = []
+        self.materialIndexPerTriangle = np.zeros(0, np.int32)
+        self.numtriangles = 0
+        self.wavelengths = None if wavelengths is None else np.asarray(wavelengths, np.float32)
+        if filepath is not None:
+            self.loadFromFile(filepath, mtlpath, wavelengths, coeff_table)
+
+    def loadFromFile(self, filepath, mtldirpath, wavelengths, coeff_table="color_tables/srgb.coeff"):
+        """``MeshS::loadFromFile`` (``MeshS.cpp:22-128``)."""
+        self._from_scene(load_obj(filepath, mtldirpath), wavelengths, coeff_table)
+
+    @classmethod
+    def from_scene(cls, scene: Scene, wavelengths=None, coeff_table=None):
+        m = cls()
+        m._from_scene(scene, wavelengths, coeff_table)
+        return m
+
+    def _from_scene(self, scene: Scene, wavelengths, coeff_table):
+        self.vertices = np.ascontiguousarray(scene.vertices, np.float32)
+        self.normals = np.ascontiguousarray(scene.normals, np.float32)
+        self.triangleIndices = np.ascontiguousarray(scene.tri, np.int32)
+        self.materialIndexPerTriangle = np.ascontiguousarray(scene.mat_idx, np.int32)
+        self.numtriangles = int(self.triangleIndices.shape[0])
+        self.scene_materials = scene.materials
+        if wavelengths is not None:
+            self.wavelengths = np.asarray(wavelengths, np.float32)
+            if coeff_table is None:
+                raise ValueError("a rgb2spec coefficient table is needed to build spectral materials")
+            model = coeff_table if isinstance(coeff_table, _r2s.RGB2Spec) else _r2s.RGB2Spec.load(coeff_table)
+            self.materials = _mat.make_materials(scene.materials, self.wavelengths, model)
+
+
+class RadMat:
+    """Stand-in for the reference's ``SpMat RadMat`` (``Eigen::SparseMatrix<float>``, ``Lightning.h:19``): the
+    matrix stays on the GPU as dense FP32 rows; this handle reads it back in either form."""
+
+    def __init__(self, optixP: "OptixPrimeFunctionality"):
+        self._p = optixP
+
+    @property
+    def shape(self):
+        return (self._p.N, self._p.N)
+
+    def rows(self, row0=None, nrows=None) -> np.ndarray:
+        r0, r1 = self._p.row_range
+        row0 = r0 if row0 is None else row0
+        nrows = (r1 - row0) if nrows is None else nrows
+        out = np.empty((nrows, self._p.N), np.float32)
+        _lib.check(_lib.lib().daisy_formfactors_read_rows(self._p._ctx, row0, nrows, _lib.fptr(out)), "formfactors_read_rows")
+        return out
+
+    def to_csc(self):
+        """(values, innerIndices, outerStarts) exactly as ``setFromTriplets`` leaves a column-major SparseMatrix."""
+        L = _lib.lib()
+        nnz = C.c_int64()
+        _lib.check(L.daisy_formfactors_to_csc(self._p._ctx, C.byref(nnz), None, None, None), "formfactors_to_csc")
+        vals = np.empty(nnz.value, np.float32)
+        inner = np.empty(nnz.value, np.int32)
+        outer = np.empty(self._p.N + 1, np.int32)
+        _lib.check(L.daisy_formfactors_to_csc(self._p._ctx, C.byref(nnz), _lib.fptr(vals), _lib.iptr(inner), _lib.iptr(outer)),
+                   "formfactors_to_csc")
+        return vals, inner, outer
+
+
+class OptixPrimeFunctionality:
+    """Reference ``OptixPrimeFunctionality`` (``OptixPrimeFunctionality.h:24-48``) on a B200.
+
+    The constructor uploads the mesh and builds the LBVH (the reference builds an OptiX Prime model,
+    ``OptixPrimeFunctionality.cpp:36-47``) and fixes the ``rands`` sample pattern (``:55-63``; the reference seeds
+    it with wall-clock time -- pass ``rands`` or ``seed`` to choose it)."""
+
+    def __init__(self, mesh: MeshS, device: int = 0, rands=None, seed: int = 1, rank: int = 0, nranks: int = 1, stream=None):
+        L = _lib.lib()
+        self.mesh = mesh
+        self.N = mesh.numtriangles
+        self._ctx = C.c_void_p()
+        v = np.ascontiguousarray(mesh.vertices, np.float32)
+        n = np.ascontiguousarray(mesh.normals, np.float32)
+        t = np.ascontiguousarray(mesh.triangleIndices, np.int32)
+        _lib.check(L.daisy_ctx_create(_lib.fptr(v), v.shape[0], _lib.fptr(n), n.shape[0], _lib.iptr(t), t.shape[0], device,
+                                      C.byref(self._ctx)), "ctx_create")
+        self.rands = np.ascontiguousarray(msvc_sample_pattern(seed, RAYS_PER_PATCH) if rands is None else rands, np.float32)
+        _lib.check(L.daisy_ctx_set_samples(self._ctx, _lib.fptr(self.rands), self.rands.shape[0]), "ctx_set_samples")
+        if nranks > 1:
+            _lib.check(L.daisy_ctx_set_partition(self._ctx, rank, nranks), "ctx_set_partition")
+        if stream is not None:
+            _lib.check(L.daisy_ctx_set_stream(self._ctx, C.c_void_p(stream)), "ctx_set_stream")
+        self.rank, self.nranks = rank, nranks
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            _lib.lib().daisy_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def row_range(self):
+        r0, r1, n = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(_lib.lib().daisy_ctx_row_range(self._ctx, C.byref(r0), C.byref(r1), C.byref(n)))
+        return r0.value, r1.value
+
+    # -- optixQuery(int number_of_rays, vector<float3>& rays, vector<Hit>& hits)              .cpp:66-81
+    def optixQuery(self, number_of_rays: int, rays, hits=None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1)
+        if rays.size < 6 * number_of_rays:
+            raise ValueError("rays holds fewer than number_of_rays origin/direction pairs")
+        if hits is None:
+            hits = np.empty(number_of_rays, HIT_DTYPE)
+        _lib.check(_lib.lib().daisy_query_closest(self._ctx, number_of_rays, _lib.fptr(rays), hits.ctypes.data), "query_closest")
+        return hits
+
+    # -- parallellism::runCalculateRadiosityMatrix(SimpleMesh&)                      parallellism.cu:4-89
+    def runCalculateRadiosityMatrix(self, row0=0, nrows=None, variant=_lib.FF_DEVICE) -> np.ndarray:
+        nrows = self.N - row0 if nrows is None else nrows
+        out = np.empty((nrows, self.N), _lib.TRIPL_DTYPE)
+        _lib.check(_lib.lib().daisy_unoccluded_rows(self._ctx, variant, row0, nrows, out.ctypes.data), "unoccluded_rows")
+        return out
+
+    # -- cudaCalculateRadiosityMatrix(SpMat&, MeshS&)                                        .cpp:6-34
+    def cudaCalculateRadiosityMatrix(self, RadMat_=None, mesh=None) -> RadMat:
+        _lib.check(_lib.lib().daisy_formfactors_build(self._ctx, _lib.FF_DEVICE), "formfactors_build")
+        return RadMat(self)
+
+    # -- calculateRadiosityMatrix(SpMat&, MeshS&)   (cuda_on = false: float pi, reciprocity)  .cpp:311-366
+    def calculateRadiosityMatrix(self, RadMat_=None, mesh=None) -> RadMat:
+        _lib.check(_lib.lib().daisy_formfactors_build(self._ctx, _lib.FF_HOST), "formfactors_build")
+        return RadMat(self)
+
+    def loadRadiosityMatrix(self, dense_rows: np.ndarray, row0: int = 0) -> RadMat:
+        """The reference's matrix-cache path (``Lightning.h:84-96``): load instead of build."""
+        a = np.ascontiguousarray(dense_rows, np.float32)
+        _lib.check(_lib.lib().daisy_formfactors_write_rows(self._ctx, row0, a.shape[0], _lib.fptr(a)), "formfactors_write_rows")
+        return RadMat(self)
+
+    def visibilityMasks(self, row0=0, nrows=None, variant=_lib.FF_DEVICE) -> np.ndarray:
+        nrows = self.N - row0 if nrows is None else nrows
+        out = np.empty((nrows, self.N), np.uint64)
+        _lib.check(_lib.lib().daisy_visibility_masks(self._ctx, variant, row0, nrows, out.ctypes.data_as(C.POINTER(C.c_uint64))),
+                   "visibility_masks")
+        return out
+
+    # -- float calculateVisibility(int originPatch, int destPatch, MeshS&, ...)               .cpp:244-271
+    def calculateVisibility(self, originPatch: int, destPatch: int, mesh=None) -> float:
+        lo, hi = (originPatch, destPatch)
+        rays = self.pair_rays(lo, hi)
+        hits = self.optixQuery(rays.shape[0], rays)
+        seen = np.count_nonzero((hits["t"] > 0) & (hits["triangleId"] == destPatch))
+        return float(np.float32(seen) / np.float32(rays.shape[0]))
+
+    def pair_rays(self, originPatch: int, destPatch: int) -> np.ndarray:
+        """The S rays of ``.cpp:253-258`` (float32, reference operation order)."""
+        m = self.mesh
+        f = np.float32
+
+        def uv2xyz(tri, u, v):
+            a, b, c = (m.vertices[m.triangleIndices[tri, k]] for k in range(3))
+            return (a + u * (b - a)) + v * (c - a)
+
+        out = np.empty((self.rands.shape[0], 6), np.float32)
+        for i, (u, v) in enumerate(self.rands):
+            o = uv2xyz(originPatch, f(u), f(v))
+            d = uv2xyz(destPatch, f(u), f(v))
+            diff = (d - o).astype(np.float32)
+            t = diff * diff
+            inv = f(1.0) / np.sqrt(f(f(t[0] + t[1]) + t[2]), dtype=np.float32)
+            n = (diff * inv).astype(np.float32)
+            out[i, :3] = o + n * f(0.000001)
+            out[i, 3:] = n
+        return out
+
+    def stats(self):
+        p, r, a, b = C.c_int64(), C.c_int64(), C.c_double(), C.c_double()
+        _lib.check(_lib.lib().daisy_formfactors_stats(self._ctx, C.byref(p), C.byref(r), C.byref(a), C.byref(b)))
+        return {"pairs_traced": p.value, "rays": r.value, "lbvh_ms": a.value, "ff_ms": b.value}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cie1931WavelengthToXYZFit(wavelength: float) -> np.ndarray:
+    """``daisy_color::cie1931WavelengthToXYZFit`` (``color.h:14-45``), double math, float32 result."""
+    wave = float(wavelength)
+    t1 = (wave - 442.0) * (0.0624 if wave < 442.0 else 0.0374)
+    t2 = (wave - 599.8) * (0.0264 if wave < 599.8 else 0.0323)
+    t3 = (wave - 501.1) * (0.0490 if wave < 501.1 else 0.0382)
+    x = 0.362 * math.exp(-0.5 * t1 * t1) + 1.056 * math.exp(-0.5 * t2 * t2) - 0.065 * math.exp(-0.5 * t3 * t3)
+    t1 = (wave - 568.8) * (0.0213 if wave < 568.8 else 0.0247)
+    t2 = (wave - 530.9) * (0.0613 if wave < 530.9 else 0.0322)
+    y = 0.821 * math.exp(-0.5 * t1 * t1) + 0.286 * math.exp(-0.5 * t2 * t2)
+    t1 = (wave - 437.0) * (0.0845 if wave < 437.0 else 0.0278)
+    t2 = (wave - 459.0) * (0.0385 if wave < 459.0 else 0.0725)
+    z = 1.217 * math.exp(-0.5 * t1 * t1) + 0.681 * math.exp(-0.5 * t2 * t2)
+    return np.array([x, y, z], np.float32)
+
+
+_XYZ2RGB = np.array([[3.240479, -1.537150, -0.498535], [-0.969256, 1.875991, 0.041556], [0.055648, -0.204043, 1.057311]], np.float32)
+
+
+def serialize_mat(path: str, vals: np.ndarray, inner: np.ndarray, outer: np.ndarray, n: int) -> None:
+    """``Lightning::SerializeMat`` byte layout (``Lightning.h:21-50``): rows, cols, nnz, outerSize, innerSize,
+    values[nnz], outerIndex[outerSize], innerIndex[nnz]."""
+    with open(path, "wb") as f:
+        f.write(struct.pack("<5i", n, n, vals.size, n, n))
+        f.write(np.ascontiguousarray(vals, np.float32).tobytes())
+        f.write(np.ascontiguousarray(outer[:n], np.int32).tobytes())
+        f.write(np.ascontiguousarray(inner, np.int32).tobytes())
+
+
+def deserialize_mat(path: str):
+    """``Lightning::DeserializeMat`` (``Lightning.h:51-74``) -> dense float32 matrix."""
+    with open(path, "rb") as f:
+        rows, cols, nnz, a, b = struct.unpack("<5i", f.read(20))
+        vals = np.frombuffer(f.read(4 * nnz), np.float32)
+        outer = np.frombuffer(f.read(4 * a), np.int32)
+        inner = np.frombuffer(f.read(4 * nnz), np.int32)
+    dense = np.zeros((rows, cols), np.float32)
+    ends = np.append(outer[1:], nnz)
+    for c in range(cols):
+        s, e = outer[c], ends[c]
+        dense[inner[s:e], c] = vals[s:e]
+    return dense
+
+
+class Lightning:
+    """Reference ``Lightning`` base (``Lightning.h:7-97``): owns ``RadMat``; ``get_lightning`` is the factory."""
+
+    numsamples = 0
+    threshold = 1e-4
+    per_band = 1
+
+    @staticmethod
+    def get_lightning(method: int, mesh: MeshS, optixP: OptixPrimeFunctionality, emissionval: float, wavelengthsvec=None,
+                      cuda_enabled: bool = False, matfile: str | None = None, converge: bool = True) -> "Lightning":
+        # Lightning.h:446-457.  BWLightning never receives cuda_on (:393,:449) => always the per-pair variant.
+        if method == 0:
+            return BWLightning(mesh, optixP, emissionval, matfile=matfile, converge=converge)
+        if method == 1:
+            return RGBLightning(mesh, optixP, emissionval, cuda_enabled, matfile, converge=converge)
+        if method == 2:
+            return SpectralLightning(mesh, optixP, emissionval, wavelengthsvec, cuda_enabled, matfile, converge=converge)
+        raise ValueError("method must be 0 (BW), 1 (RGB) or 2 (Spectral)")
+
+    # -- shared plumbing -------------------------------------------------------------------------------
+    def _init(self, mesh, optixP, E, M, cuda_on, matfile, converge):
+        self.mesh_, self.optixP = mesh, optixP
+        self.cuda_on = cuda_on
+        self.numpatches = mesh.numtriangles
+        if matfile is None:
+            self.initMat(mesh, optixP)
+        else:
+            self.initMatFromFile(mesh, optixP, matfile)
+        E = np.ascontiguousarray(E, np.float32)
+        M = np.ascontiguousarray(M, np.float32)
+        mat = np.ascontiguousarray(mesh.materialIndexPerTriangle, np.int32)
+        self.K = E.shape[0]
+        self._s = C.c_void_p()
+        _lib.check(_lib.lib().daisy_solver_create(optixP._ctx, self.K, _lib.fptr(E), _lib.fptr(M), M.shape[0], _lib.iptr(mat),
+                                                  C.byref(self._s)), "solver_create")
+        self.emission = E
+        self.reset()
+        if converge:
+            self.converge_lightning()
+
+    def initMat(self, mesh, optixP):  # Lightning.h:75-83
+        self.RadMat = optixP.cudaCalculateRadiosityMatrix() if self.cuda_on else optixP.calculateRadiosityMatrix()
+
+    def initMatFromFile(self, mesh, optixP, matfile):  # Lightning.h:84-96
+        if os.path.exists(matfile):
+            self.RadMat = optixP.loadRadiosityMatrix(deserialize_mat(matfile))
+        else:
+            self.initMat(mesh, optixP)
+            serialize_mat(matfile, *self.RadMat.to_csc(), mesh.numtriangles)
+
+    def close(self):
+        if getattr(self, "_s", None):
+            _lib.lib().daisy_solver_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def numpasses(self) -> int:
+        return int(_lib.lib().daisy_solver_numpasses(self._s))
+
+    def band_sums(self) -> np.ndarray:
+        out = np.zeros(self.K, np.float64)
+        _lib.check(_lib.lib().daisy_solver_band_sums(self._s, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def read(self):
+        """(lightningvalues, residualvector), each K x N band-major."""
+        r0, r1 = self.optixP.row_range
+        B = np.empty((self.K, r1 - r0), np.float32)
+        R = np.empty((self.K, r1 - r0), np.float32)
+        _lib.check(_lib.lib().daisy_solver_read(self._s, _lib.fptr(B), _lib.fptr(R)), "solver_read")
+        return B, R
+
+    @property
+    def lightningvalues(self):
+        return self.read()[0]
+
+    @property
+    def residualvector(self):
+        return self.read()[1]
+
+    def reset(self):
+        _lib.check(_lib.lib().daisy_solver_reset(self._s), "solver_reset")
+        self._after_update()
+
+    def increment_lightpass(self):
+        sums = np.zeros(self.K, np.float64)
+        _lib.check(_lib.lib().daisy_solver_step(self._s, sums.ctypes.data_as(C.POINTER(C.c_double))), "solver_step")
+        self._after_update()
+        return sums
+
+    def converge_lightning(self, max_passes: int = 0):
+        passes = C.c_int()
+        _lib.check(_lib.lib().daisy_solver_converge(self._s, float(self.threshold), int(self.per_band), max_passes, C.byref(passes)),
+                   "solver_converge")
+        self._after_update()
+        return passes.value
+
+    def _after_update(self):
+        pass
+
+    def get_color_of_patch(self, index: int) -> np.ndarray:
+        raise NotImplementedError
+
+
+class SpectralLightning(Lightning):
+    """``SpectralLightning`` (``Lightning.h:99-295``): stop when the residual summed over all bands <= 200."""
+
+    threshold, per_band = 200.0, 0
+
+    def __init__(self, mesh, optixP, emissionval, wavelengthsvec, cuda_enabled=False, matfile=None, converge=True):
+        self.numsamples = len(wavelengthsvec)
+        self.xyz_per_wavelength = np.stack([cie1931WavelengthToXYZFit(w) for w in wavelengthsvec])  # :245-253
+        self.emission_value = emissionval
+        E, M = _mat.spectral_inputs(mesh.materials, mesh.materialIndexPerTriangle, emissionval)  # :263-292
+        self._cache = None
+        self._init(mesh, optixP, E, M, cuda_enabled, matfile, converge)
+
+    def _after_update(self):
+        self._cache = None
+
+    def update_color_cache(self):  # Lightning.h:168-183 (xyz starts from zero here; the reference leaves it uninitialised)
+        B = self.lightningvalues
+        xyz = np.zeros((B.shape[1], 3), np.float32)
+        for j in range(self.numsamples):
+            xyz += self.xyz_per_wavelength[j][None, :] * B[j][:, None]
+        rgb = np.stack([
+            _XYZ2RGB[0, 0] * xyz[:, 0] + _XYZ2RGB[0, 1] * xyz[:, 1] + _XYZ2RGB[0, 2] * xyz[:, 2],
+            _XYZ2RGB[1, 0] * xyz[:, 0] + _XYZ2RGB[1, 1] * xyz[:, 1] + _XYZ2RGB[1, 2] * xyz[:, 2],
+            _XYZ2RGB[2, 0] * xyz[:, 0] + _XYZ2RGB[2, 1] * xyz[:, 1] + _XYZ2RGB[2, 2] * xyz[:, 2]], axis=1).astype(np.float32)
+        maxval = rgb.max(axis=1)
+        scale = np.where(maxval > 1, maxval, np.float32(1))
+        self._cache = (rgb / scale[:, None]).astype(np.float32)
+
+    def get_color_of_patch(self, index):
+        if self._cache is None:
+            self.update_color_cache()
+        return self._cache[index]
+
+
+class RGBLightning(Lightning):
+    """``RGBLightning`` (``Lightning.h:298-384``): stop when every channel's residual sum <= 1e-4."""
+
+    threshold, per_band = 1e-4, 1
+
+    def __init__(self, mesh, optixP, emissionval, cuda_enabled=False, matfile=None, converge=True):
+        self.numsamples = 3
+        E, M = _mat.rgb_inputs(mesh.materials, mesh.materialIndexPerTriangle, emissionval)  # :359-382
+        self._init(mesh, optixP, E, M, cuda_enabled, matfile, converge)
+
+    def get_color_of_patch(self, index):
+        return self.lightningvalues[:, index].copy()
+
+
+class BWLightning(Lightning):
+    """``BWLightning`` (``Lightning.h:386-443``): residual = F residual, stop at sum <= 1e-4."""
+
+    threshold, per_band = 1e-4, 1
+
+    def __init__(self, mesh, optixP, emissionval, matfile=None, converge=True):
+        self.numsamples = 1
+        E, M = _mat.bw_inputs(mesh.materials, mesh.materialIndexPerTriangle, emissionval)  # :434-442
+        self._init(mesh, optixP, E, M, False, matfile, converge)
+
+    def get_color_of_patch(self, index):
+        v = self.lightningvalues[0, index]
+        return np.array([v, v, v], np.float32)

@@ -1,0 +1,310 @@
+// api.cu -- the C-ABI of include/daisy_b200.h for the context (mesh, LBVH, ray query, form factors).
+// The solver half of the ABI lives in gather.cu.
+#include "daisy_common.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <vector>
+
+static thread_local char g_err[1024] = "";
+
+void daisy_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *daisy_last_error(void) { return g_err; }
+extern "C" int daisy_version(void) { return 100; }
+extern "C" int daisy_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static void free_ctx(daisy_ctx *c) {
+    if (!c) return;
+    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_geom);
+    cudaFree(c->d_nodes); cudaFree(c->d_F);
+    delete c;
+}
+
+static void set_partition(daisy_ctx *c, int rank, int nranks) {
+    c->rank = rank; c->nranks = nranks;
+    int n = (c->N + nranks - 1) / nranks;
+    n = ((n + 3) / 4) * 4;
+    if (n < 4) n = 4;
+    c->rows_per_rank = n;
+    c->row0 = (int)fmin((double)c->N, (double)rank * n);
+    c->row1 = (int)fmin((double)c->N, (double)(rank + 1) * n);
+    int64_t ncols = (int64_t)nranks * n;
+    if (ncols < c->N) ncols = c->N;
+    c->ldF = ((ncols + 31) / 32) * 32;
+}
+
+extern "C" int daisy_ctx_create(const float *vertices, int nv, const float *normals, int nn, const int32_t *tri_idx, int ntri,
+                                int device, daisy_ctx **out) {
+    DZ_REQUIRE(out, DAISY_E_INVALID, "daisy_ctx_create: null out pointer");
+    *out = nullptr;
+    DZ_REQUIRE(nv >= 0 && nn >= 0 && ntri >= 0, DAISY_E_INVALID, "daisy_ctx_create: negative count");
+    DZ_REQUIRE(ntri == 0 || (vertices && normals && tri_idx), DAISY_E_INVALID, "daisy_ctx_create: null array");
+    for (int i = 0; i < ntri; i++)
+        for (int k = 0; k < 6; k++) {
+            int v = tri_idx[6 * (size_t)i + k];
+            DZ_REQUIRE(v >= 0 && v < (k < 3 ? nv : nn), DAISY_E_INVALID, "daisy_ctx_create: triangle index out of range");
+        }
+    int ndev = 0;
+    DZ_CUDA(cudaGetDeviceCount(&ndev));
+    DZ_REQUIRE(device >= 0 && device < ndev, DAISY_E_INVALID, "daisy_ctx_create: no such CUDA device");
+    DZ_CUDA(cudaSetDevice(device));
+    daisy_ctx *c = new daisy_ctx();
+    c->device = device; c->N = ntri; c->nv = nv; c->nn = nn;
+    cudaDeviceProp prop;
+    DZ_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    set_partition(c, 0, 1);
+    // scene bounds over the vertices the triangles use (host: the inputs are host arrays anyway)
+    for (int d = 0; d < 3; d++) { c->scene_lo[d] = INFINITY; c->scene_hi[d] = -INFINITY; }
+    for (int i = 0; i < ntri; i++)
+        for (int k = 0; k < 3; k++) {
+            const float *p = vertices + 3 * (size_t)tri_idx[6 * (size_t)i + k];
+            for (int d = 0; d < 3; d++) { c->scene_lo[d] = fminf(c->scene_lo[d], p[d]); c->scene_hi[d] = fmaxf(c->scene_hi[d], p[d]); }
+        }
+    float ext = 0.f;
+    for (int d = 0; d < 3; d++) if (ntri) ext = fmaxf(ext, c->scene_hi[d] - c->scene_lo[d]);
+    c->pad = 1e-4f * ext; // conservative box padding; results never depend on it (tests compare with brute force)
+#define CC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { daisy_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); free_ctx(c); return DAISY_E_CUDA; } } while (0)
+    CC(cudaMalloc(&c->d_vertices, sizeof(float) * 3 * (size_t)(nv > 0 ? nv : 1)));
+    CC(cudaMalloc(&c->d_normals, sizeof(float) * 3 * (size_t)(nn > 0 ? nn : 1)));
+    CC(cudaMalloc(&c->d_tri, sizeof(int) * 6 * (size_t)(ntri > 0 ? ntri : 1)));
+    CC(cudaMalloc(&c->d_geom, sizeof(PatchGeom) * (size_t)(ntri > 0 ? ntri : 1)));
+    if (nv) CC(cudaMemcpy(c->d_vertices, vertices, sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice));
+    if (nn) CC(cudaMemcpy(c->d_normals, normals, sizeof(float) * 3 * (size_t)nn, cudaMemcpyHostToDevice));
+    if (ntri) CC(cudaMemcpy(c->d_tri, tri_idx, sizeof(int) * 6 * (size_t)ntri, cudaMemcpyHostToDevice));
+#undef CC
+    int rc = dz_build_lbvh(c);
+    if (!rc) rc = dz_precompute_geom(c);
+    if (!rc && cudaStreamSynchronize(c->stream) != cudaSuccess) { daisy_set_error("daisy_ctx_create: %s", cudaGetErrorString(cudaGetLastError())); rc = DAISY_E_CUDA; }
+    if (rc) { free_ctx(c); return rc; }
+    *out = c;
+    return DAISY_OK;
+}
+
+extern "C" void daisy_ctx_destroy(daisy_ctx *ctx) {
+    if (ctx) cudaSetDevice(ctx->device);
+    free_ctx(ctx);
+}
+
+extern "C" int daisy_ctx_set_samples(daisy_ctx *ctx, const float *uv, int S) {
+    DZ_REQUIRE(ctx && uv, DAISY_E_INVALID, "daisy_ctx_set_samples: null argument");
+    DZ_REQUIRE(S >= 1 && S <= DAISY_MAX_SAMPLES, DAISY_E_INVALID, "daisy_ctx_set_samples: S must be in [1,64]");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    memset(ctx->h_uv, 0, sizeof(ctx->h_uv));
+    memcpy(ctx->h_uv, uv, sizeof(float) * 2 * (size_t)S);
+    ctx->S = S;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_ctx_set_partition(daisy_ctx *ctx, int rank, int nranks) {
+    DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_ctx_set_partition: null context");
+    DZ_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, DAISY_E_INVALID, "daisy_ctx_set_partition: bad rank/nranks");
+    DZ_REQUIRE(!ctx->have_F, DAISY_E_STATE, "daisy_ctx_set_partition: form factors already built");
+    set_partition(ctx, rank, nranks);
+    return DAISY_OK;
+}
+
+extern "C" int daisy_ctx_row_range(daisy_ctx *ctx, int *row0, int *row1, int *rows_per_rank) {
+    DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_ctx_row_range: null context");
+    if (row0) *row0 = ctx->row0;
+    if (row1) *row1 = ctx->row1;
+    if (rows_per_rank) *rows_per_rank = ctx->rows_per_rank;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_ctx_set_stream(daisy_ctx *ctx, void *cuda_stream) {
+    DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_ctx_set_stream: null context");
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return DAISY_OK;
+}
+
+// ---- closest hit -------------------------------------------------------------------------------------------
+extern "C" int daisy_query_closest_device(daisy_ctx *ctx, int n, const float *d_rays6, daisy_hit *d_hits) {
+    DZ_REQUIRE(ctx && (n == 0 || (d_rays6 && d_hits)), DAISY_E_INVALID, "daisy_query_closest_device: null argument");
+    DZ_REQUIRE(n >= 0, DAISY_E_INVALID, "daisy_query_closest_device: negative ray count");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    int rc = dz_launch_closest(ctx, n, d_rays6, d_hits);
+    if (rc) return rc;
+    DZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DAISY_OK;
+}
+
+extern "C" int daisy_query_closest(daisy_ctx *ctx, int n, const float *rays6, daisy_hit *hits) {
+    DZ_REQUIRE(ctx && (n == 0 || (rays6 && hits)), DAISY_E_INVALID, "daisy_query_closest: null argument");
+    DZ_REQUIRE(n >= 0, DAISY_E_INVALID, "daisy_query_closest: negative ray count");
+    if (n == 0) return DAISY_OK;
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    float *d_r = nullptr;
+    daisy_hit *d_h = nullptr;
+    DZ_CUDA(cudaMalloc(&d_r, sizeof(float) * 6 * (size_t)n));
+    cudaError_t e = cudaMalloc(&d_h, sizeof(daisy_hit) * (size_t)n);
+    if (e != cudaSuccess) { cudaFree(d_r); daisy_set_error("daisy_query_closest: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
+    int rc = DAISY_OK;
+    e = cudaMemcpyAsync(d_r, rays6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = dz_launch_closest(ctx, n, d_r, d_h);
+    if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(hits, d_h, sizeof(daisy_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_r); cudaFree(d_h);
+    if (e != cudaSuccess) { daisy_set_error("daisy_query_closest: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
+    return rc;
+}
+
+// ---- form factors --------------------------------------------------------------------------------------------
+extern "C" int daisy_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_tripl *out) {
+    DZ_REQUIRE(ctx && out, DAISY_E_INVALID, "daisy_unoccluded_rows: null argument");
+    DZ_REQUIRE(variant == DAISY_FF_DEVICE || variant == DAISY_FF_HOST, DAISY_E_INVALID, "daisy_unoccluded_rows: bad variant");
+    DZ_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= ctx->N, DAISY_E_INVALID, "daisy_unoccluded_rows: rows out of range");
+    if (nrows == 0 || ctx->N == 0) return DAISY_OK;
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    const int N = ctx->N;
+    int chunk = (int)fmax(1.0, fmin(4096.0, (double)(256u << 20) / (16.0 * N))); // ~256 MB of triplets at a time
+    daisy_tripl *d = nullptr;
+    DZ_CUDA(cudaMalloc(&d, sizeof(daisy_tripl) * (size_t)chunk * N));
+    int rc = DAISY_OK;
+    for (int r = row0; r < row0 + nrows && !rc; r += chunk) {
+        int nr = (row0 + nrows - r) < chunk ? (row0 + nrows - r) : chunk;
+        rc = dz_unoccluded_rows(ctx, variant, r, nr, d);
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(out + (size_t)(r - row0) * N, d, sizeof(daisy_tripl) * (size_t)nr * N, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { daisy_set_error("daisy_unoccluded_rows: %s", cudaGetErrorString(e)); rc = DAISY_E_CUDA; }
+        }
+    }
+    cudaFree(d);
+    return rc;
+}
+
+static int ensure_F(daisy_ctx *ctx) {
+    if (ctx->d_F) return DAISY_OK;
+    size_t rows = (size_t)(ctx->row1 - ctx->row0);
+    size_t bytes = sizeof(float) * (rows ? rows : 1) * (size_t)ctx->ldF;
+    DZ_CUDA(cudaMalloc(&ctx->d_F, bytes));
+    DZ_CUDA(cudaMemsetAsync(ctx->d_F, 0, bytes, ctx->stream)); // padding columns stay zero for the gather
+    return DAISY_OK;
+}
+
+extern "C" int daisy_formfactors_build(daisy_ctx *ctx, int variant) {
+    DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_formfactors_build: null context");
+    DZ_REQUIRE(variant == DAISY_FF_DEVICE || variant == DAISY_FF_HOST, DAISY_E_INVALID, "daisy_formfactors_build: bad variant");
+    DZ_REQUIRE(ctx->S >= 1, DAISY_E_STATE, "daisy_formfactors_build: call daisy_ctx_set_samples first");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_F(ctx);
+    if (rc) return rc;
+    rc = dz_set_samples_const(ctx);
+    if (rc) return rc;
+    rc = dz_build_formfactors(ctx, variant, nullptr, 0, 0, true);
+    if (rc) return rc;
+    ctx->have_F = true;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_formfactors_ld(daisy_ctx *ctx, int64_t *ld_out) {
+    DZ_REQUIRE(ctx && ld_out, DAISY_E_INVALID, "daisy_formfactors_ld: null argument");
+    *ld_out = ctx->ldF;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_formfactors_read_rows(daisy_ctx *ctx, int row0, int nrows, float *out) {
+    DZ_REQUIRE(ctx && (nrows == 0 || out), DAISY_E_INVALID, "daisy_formfactors_read_rows: null argument");
+    DZ_REQUIRE(ctx->have_F, DAISY_E_STATE, "daisy_formfactors_read_rows: no form factors yet");
+    DZ_REQUIRE(nrows >= 0 && row0 >= ctx->row0 && row0 + nrows <= ctx->row1, DAISY_E_INVALID, "daisy_formfactors_read_rows: rows outside this context's range");
+    if (nrows == 0) return DAISY_OK;
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    DZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    DZ_CUDA(cudaMemcpy2D(out, sizeof(float) * (size_t)ctx->N, ctx->d_F + (size_t)(row0 - ctx->row0) * ctx->ldF, sizeof(float) * (size_t)ctx->ldF,
+                         sizeof(float) * (size_t)ctx->N, (size_t)nrows, cudaMemcpyDeviceToHost));
+    return DAISY_OK;
+}
+
+extern "C" int daisy_formfactors_write_rows(daisy_ctx *ctx, int row0, int nrows, const float *in) {
+    DZ_REQUIRE(ctx && (nrows == 0 || in), DAISY_E_INVALID, "daisy_formfactors_write_rows: null argument");
+    DZ_REQUIRE(nrows >= 0 && row0 >= ctx->row0 && row0 + nrows <= ctx->row1, DAISY_E_INVALID, "daisy_formfactors_write_rows: rows outside this context's range");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_F(ctx);
+    if (rc) return rc;
+    if (nrows)
+        DZ_CUDA(cudaMemcpy2DAsync(ctx->d_F + (size_t)(row0 - ctx->row0) * ctx->ldF, sizeof(float) * (size_t)ctx->ldF, in, sizeof(float) * (size_t)ctx->N,
+                                  sizeof(float) * (size_t)ctx->N, (size_t)nrows, cudaMemcpyHostToDevice, ctx->stream));
+    DZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_F = true;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_formfactors_to_csc(daisy_ctx *ctx, int64_t *nnz, float *values, int32_t *inner_idx, int32_t *outer_ptr) {
+    DZ_REQUIRE(ctx && nnz, DAISY_E_INVALID, "daisy_formfactors_to_csc: null argument");
+    DZ_REQUIRE(ctx->have_F, DAISY_E_STATE, "daisy_formfactors_to_csc: no form factors yet");
+    DZ_REQUIRE(ctx->nranks == 1, DAISY_E_STATE, "daisy_formfactors_to_csc: single-GPU contexts only");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    const int N = ctx->N;
+    // host-side conversion in row chunks (this is the hand-back path for callers that still want an Eigen SpMat)
+    std::vector<int64_t> colcount((size_t)N + 1, 0);
+    const int chunk = (int)fmax(1.0, fmin((double)N, (double)(128u << 20) / (4.0 * (N ? N : 1))));
+    std::vector<float> rows((size_t)chunk * (N ? N : 1));
+    for (int r = 0; r < N; r += chunk) {
+        int nr = (N - r) < chunk ? (N - r) : chunk;
+        int rc = daisy_formfactors_read_rows(ctx, r, nr, rows.data());
+        if (rc) return rc;
+        for (int i = 0; i < nr; i++)
+            for (int c = 0; c < N; c++)
+                if (rows[(size_t)i * N + c] != 0.0f) colcount[(size_t)c + 1]++;
+    }
+    for (int c = 0; c < N; c++) colcount[(size_t)c + 1] += colcount[c];
+    *nnz = colcount[N];
+    if (!values) return DAISY_OK;
+    DZ_REQUIRE(inner_idx && outer_ptr, DAISY_E_INVALID, "daisy_formfactors_to_csc: null index arrays");
+    DZ_REQUIRE(*nnz <= 0x7fffffffLL, DAISY_E_INVALID, "daisy_formfactors_to_csc: more non-zeros than Eigen's int index can hold");
+    for (int c = 0; c <= N; c++) outer_ptr[c] = (int32_t)colcount[c];
+    std::vector<int64_t> fill(colcount.begin(), colcount.end() - 1);
+    for (int r = 0; r < N; r += chunk) {
+        int nr = (N - r) < chunk ? (N - r) : chunk;
+        int rc = daisy_formfactors_read_rows(ctx, r, nr, rows.data());
+        if (rc) return rc;
+        for (int i = 0; i < nr; i++)
+            for (int c = 0; c < N; c++) {
+                float v = rows[(size_t)i * N + c];
+                if (v != 0.0f) { int64_t p = fill[c]++; values[p] = v; inner_idx[p] = r + i; } // rows ascend => sorted inner indices
+            }
+    }
+    return DAISY_OK;
+}
+
+extern "C" int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int nrows, uint64_t *out) {
+    DZ_REQUIRE(ctx && (nrows == 0 || out), DAISY_E_INVALID, "daisy_visibility_masks: null argument");
+    DZ_REQUIRE(variant == DAISY_FF_DEVICE || variant == DAISY_FF_HOST, DAISY_E_INVALID, "daisy_visibility_masks: bad variant");
+    DZ_REQUIRE(ctx->S >= 1, DAISY_E_STATE, "daisy_visibility_masks: call daisy_ctx_set_samples first");
+    DZ_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= ctx->N, DAISY_E_INVALID, "daisy_visibility_masks: rows out of range");
+    if (nrows == 0 || ctx->N == 0) return DAISY_OK;
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    int rc = dz_set_samples_const(ctx);
+    if (rc) return rc;
+    uint64_t *d = nullptr;
+    size_t bytes = sizeof(uint64_t) * (size_t)nrows * ctx->N;
+    DZ_CUDA(cudaMalloc(&d, bytes));
+    cudaError_t e = cudaMemsetAsync(d, 0, bytes, ctx->stream);
+    if (e == cudaSuccess) rc = dz_build_formfactors(ctx, variant, d, row0, row0 + nrows, false);
+    if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { daisy_set_error("daisy_visibility_masks: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
+    return rc;
+}
+
+extern "C" int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *rays, double *lbvh_ms, double *ff_ms) {
+    DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_formfactors_stats: null context");
+    if (pairs_traced) *pairs_traced = ctx->pairs_traced;
+    if (rays) *rays = ctx->pairs_traced * (int64_t)ctx->S;
+    if (lbvh_ms) *lbvh_ms = ctx->lbvh_ms;
+    if (ff_ms) *ff_ms = ctx->ff_ms;
+    return DAISY_OK;
+}

@@ -1,0 +1,167 @@
+// daisy_common.cuh -- shared device helpers of the sm_100a form-factor / gather library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/daisy_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing (C-ABI never throws; the C++ shim above it reproduces the reference's print-and-continue)
+void daisy_set_error(const char *fmt, ...);
+#define DZ_CUDA(call)                                                                                    \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            daisy_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));       \
+            return DAISY_E_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+#define DZ_REQUIRE(cond, code, msg)                         \
+    do {                                                    \
+        if (!(cond)) { daisy_set_error("%s", msg); return code; } \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// Exactly-rounded FP32 ops that ptxas may never contract into FMAs.  The reference's host build (MSVC x64,
+// /fp:precise) evaluates every glm expression as separate IEEE mul/add; parity with it (and with the CPU oracle)
+// is bit-exact only if the device does the same, so every result-defining expression goes through these.
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fd(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsq(float a) { return __fsqrt_rn(a); }
+
+struct f3 { float x, y, z; };
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 e_sub(f3 a, f3 b) { return mk3(fs(a.x, b.x), fs(a.y, b.y), fs(a.z, b.z)); }
+__device__ __forceinline__ f3 e_add(f3 a, f3 b) { return mk3(fa(a.x, b.x), fa(a.y, b.y), fa(a.z, b.z)); }
+__device__ __forceinline__ f3 e_scale(f3 a, float s) { return mk3(fm(a.x, s), fm(a.y, s), fm(a.z, s)); }
+// glm compute_dot<tvec3>: tmp = x*y; tmp.x + tmp.y + tmp.z          (glm/detail/func_geometric.inl:54-61)
+__device__ __forceinline__ float e_dot(f3 a, f3 b) { return fa(fa(fm(a.x, b.x), fm(a.y, b.y)), fm(a.z, b.z)); }
+// glm compute_cross                                                  (glm/detail/func_geometric.inl:74-85)
+__device__ __forceinline__ f3 e_cross(f3 x, f3 y) {
+    return mk3(fs(fm(x.y, y.z), fm(y.y, x.z)), fs(fm(x.z, y.x), fm(y.z, x.x)), fs(fm(x.x, y.y), fm(y.x, x.y)));
+}
+// glm normalize = v * (1 / sqrt(dot(v,v)))                           (glm/detail/func_geometric.inl:88-95)
+__device__ __forceinline__ f3 e_normalize(f3 a) { return e_scale(a, fd(1.0f, fsq(e_dot(a, a)))); }
+// calculateSurface: 0.5 * length(cross(b-a, c-a)), 0.5 a double literal (VS/parallellism.cu:209-214); the double
+// product rounded to float equals the float product with 0.5f (scaling by a power of two, RN both ways)
+__device__ __forceinline__ float e_surface(f3 a, f3 b, f3 c) {
+    f3 cr = e_cross(e_sub(b, a), e_sub(c, a));
+    return fm(0.5f, fsq(e_dot(cr, cr)));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Watertight ray/triangle test (Woop, Benthin, Wald, JCGT 2013), FP32, no culling, t = T/det by IEEE division.
+// Stands in for OptiX Prime's closed-source intersector; the CPU oracle states the same arithmetic.
+struct WRay {
+    f3 o;           // origin
+    int kx, ky, kz; // axis permutation, kz = dominant direction axis
+    float Sx, Sy, Sz;
+};
+__device__ __forceinline__ float comp(const f3 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+__device__ __forceinline__ WRay wray_setup(f3 o, f3 d) {
+    WRay w;
+    w.o = o;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int kz = (ax >= ay && ax >= az) ? 0 : ((ay >= az) ? 1 : 2);
+    int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
+    float dz = comp(d, kz);
+    if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }
+    w.kx = kx; w.ky = ky; w.kz = kz;
+    w.Sx = fd(comp(d, kx), dz);
+    w.Sy = fd(comp(d, ky), dz);
+    w.Sz = fd(1.0f, dz);
+    return w;
+}
+
+// returns true on a hit with finite t > 0; u,v = barycentric weights of vertices 1 and 2 (HIT_T_TRIID_U_V)
+__device__ __forceinline__ bool wray_tri(const WRay &w, f3 va, f3 vb, f3 vc, float &t, float &u, float &v) {
+    f3 A = e_sub(va, w.o), B = e_sub(vb, w.o), C = e_sub(vc, w.o);
+    float Akz = comp(A, w.kz), Bkz = comp(B, w.kz), Ckz = comp(C, w.kz);
+    float Ax = fs(comp(A, w.kx), fm(w.Sx, Akz)), Ay = fs(comp(A, w.ky), fm(w.Sy, Akz));
+    float Bx = fs(comp(B, w.kx), fm(w.Sx, Bkz)), By = fs(comp(B, w.ky), fm(w.Sy, Bkz));
+    float Cx = fs(comp(C, w.kx), fm(w.Sx, Ckz)), Cy = fs(comp(C, w.ky), fm(w.Sy, Ckz));
+    float U = fs(fm(Cx, By), fm(Cy, Bx));
+    float V = fs(fm(Ax, Cy), fm(Ay, Cx));
+    float W = fs(fm(Bx, Ay), fm(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = __double2float_rn(__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx)));
+        V = __double2float_rn(__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx)));
+        W = __double2float_rn(__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax)));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    float det = fa(fa(U, V), W);
+    if (det == 0.0f) return false;
+    float Az = fm(w.Sz, Akz), Bz = fm(w.Sz, Bkz), Cz = fm(w.Sz, Ckz);
+    float T = fa(fa(fm(U, Az), fm(V, Bz)), fm(W, Cz));
+    float tt = fd(T, det);
+    if (!(tt > 0.0f) || isinf(tt)) return false;
+    t = tt; u = fd(V, det); v = fd(W, det);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BVH node (64 B): both child boxes live in the parent, so one node fetch decides both descents.
+// child < 0 => leaf holding triangle ~child.
+struct __align__(16) BvhNode {
+    float4 a; // L.lo.x L.lo.y L.lo.z L.hi.x
+    float4 b; // L.hi.y L.hi.z R.lo.x R.lo.y
+    float4 c; // R.lo.z R.hi.x R.hi.y R.hi.z
+    int4 d;   // left, right, 0, 0
+};
+
+// conservative slab test against [0, tmax]; boxes are padded at build time, fminf/fmaxf drop the NaN of 0*inf
+__device__ __forceinline__ bool ray_box(f3 o, f3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz,
+                                        float tmax, float &tnear) {
+    float t0x = (lox - o.x) * inv.x, t1x = (hix - o.x) * inv.x;
+    float t0y = (loy - o.y) * inv.y, t1y = (hiy - o.y) * inv.y;
+    float t0z = (loz - o.z) * inv.z, t1z = (hiz - o.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+    tnear = tn;
+    return tn <= tf * 1.00001f + 1e-30f;
+}
+
+// per-triangle vertex record (48 B): float4 a, b, c (w unused)
+struct __align__(16) TriVerts { float4 a, b, c; };
+// per-patch record for the 4x4 rule (80 B): 4 sub-centroids with sub-areas in w, then normal with area in w
+struct __align__(16) PatchGeom { float4 s[4]; float4 n; };
+
+__device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
+
+// ---------------------------------------------------------------------------------------------------------
+struct daisy_ctx {
+    int device = 0;
+    cudaStream_t stream = 0;
+    int N = 0, nv = 0, nn = 0;
+    int rank = 0, nranks = 1, rows_per_rank = 0, row0 = 0, row1 = 0;
+    int S = 0;
+    float h_uv[2 * DAISY_MAX_SAMPLES];
+    // device mesh
+    float *d_vertices = nullptr, *d_normals = nullptr;
+    int *d_tri = nullptr;
+    TriVerts *d_triverts = nullptr;
+    PatchGeom *d_geom = nullptr;
+    // LBVH
+    BvhNode *d_nodes = nullptr;
+    int root = 0;
+    float scene_lo[3], scene_hi[3], pad = 0.f;
+    double lbvh_ms = 0.0;
+    // form factors
+    float *d_F = nullptr; // (row1-row0) x ldF
+    int64_t ldF = 0;
+    bool have_F = false;
+    int64_t pairs_traced = 0;
+    double ff_ms = 0.0;
+    int num_sms = 148;
+};
+
+int dz_build_lbvh(daisy_ctx *ctx);                                   // bvh.cu
+int dz_launch_closest(daisy_ctx *ctx, int n, const float *d_rays, daisy_hit *d_hits); // bvh.cu
+int dz_precompute_geom(daisy_ctx *ctx);                              // formfactor.cu
+int dz_set_samples_const(daisy_ctx *ctx);                            // formfactor.cu
+int dz_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_tripl *d_out); // formfactor.cu
+int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mrow0, int mrow1, bool write_F); // formfactor.cu

@@ -1,0 +1,413 @@
+// formfactor.cu -- unoccluded 4x4 form-factor rule + 50-sample visibility, fused, writing dense FP32 rows.
+//
+// Replaces (reference "visual studio/"):
+//   parallellism::calculateRow / p2pFormfactor / calcPointFormfactor     parallellism.cu:91-227
+//   OptixPrimeFunctionality::calculateAllVisibility                      OptixPrimeFunctionality.cpp:169-242
+//   OptixPrimeFunctionality::calculateRadiosityMatrix (cuda_on=false)    OptixPrimeFunctionality.cpp:311-366
+// The reference materialises N^2 16-byte triplets on the host, generates 24-byte rays on one CPU thread, ships
+// them to OptiX Prime in 4M-ray batches and reduces 16-byte hits on the host.  Here one kernel owns a 64x64 tile
+// of the upper triangle: it evaluates the 16 sub-patch terms once (they serve F(r,c) and F(c,r)), generates the
+// rays in registers, walks the LBVH, and writes both mirrored tiles coalesced through shared memory.
+#include "daisy_common.cuh"
+#include <math.h>
+
+#define TILE 64
+#define FF_THREADS 256
+#define PI_D 3.14159265358979323846
+#define PI_F 3.14159265358979323846f
+
+__constant__ float c_uv[2 * DAISY_MAX_SAMPLES];
+
+int dz_set_samples_const(daisy_ctx *ctx) {
+    DZ_CUDA(cudaMemcpyToSymbolAsync(c_uv, ctx->h_uv, sizeof(float) * 2 * DAISY_MAX_SAMPLES, 0, cudaMemcpyHostToDevice, ctx->stream));
+    DZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DAISY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-patch precompute: divideInFourTriangles (parallellism.cu:153-172), calculateCentre (:181-186),
+// calculateSurface (:209-227), avgNormal (:188-195).  Same operation order as the reference, no FMA.
+__global__ void k_patch_geom(const float *__restrict__ vertices, const float *__restrict__ normals, const int *__restrict__ tri,
+                             int N, PatchGeom *__restrict__ geom) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int *t = tri + 6 * (size_t)p;
+    f3 a = mk3(vertices[3 * (size_t)t[0]], vertices[3 * (size_t)t[0] + 1], vertices[3 * (size_t)t[0] + 2]);
+    f3 b = mk3(vertices[3 * (size_t)t[1]], vertices[3 * (size_t)t[1] + 1], vertices[3 * (size_t)t[1] + 2]);
+    f3 c = mk3(vertices[3 * (size_t)t[2]], vertices[3 * (size_t)t[2] + 1], vertices[3 * (size_t)t[2] + 2]);
+    f3 n0 = mk3(normals[3 * (size_t)t[3]], normals[3 * (size_t)t[3] + 1], normals[3 * (size_t)t[3] + 2]);
+    f3 n1 = mk3(normals[3 * (size_t)t[4]], normals[3 * (size_t)t[4] + 1], normals[3 * (size_t)t[4] + 2]);
+    f3 n2 = mk3(normals[3 * (size_t)t[5]], normals[3 * (size_t)t[5] + 1], normals[3 * (size_t)t[5] + 2]);
+    // innerA = ((b - a) / 2.0f) + a ; innerC = ((c - a) / 2.0f) + a ; innerB = ((b - c) / 2.0f) + c
+    f3 ba = e_sub(b, a), ca = e_sub(c, a), bc = e_sub(b, c);
+    f3 iA = e_add(mk3(fd(ba.x, 2.0f), fd(ba.y, 2.0f), fd(ba.z, 2.0f)), a);
+    f3 iC = e_add(mk3(fd(ca.x, 2.0f), fd(ca.y, 2.0f), fd(ca.z, 2.0f)), a);
+    f3 iB = e_add(mk3(fd(bc.x, 2.0f), fd(bc.y, 2.0f), fd(bc.z, 2.0f)), c);
+    f3 T[4][3] = { { a, iC, iA }, { iC, c, iB }, { iA, iB, b }, { iA, iB, iC } };
+    PatchGeom g;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        f3 s = e_add(e_add(T[i][0], T[i][1]), T[i][2]);
+        g.s[i] = make_float4(fd(s.x, 3.0f), fd(s.y, 3.0f), fd(s.z, 3.0f), e_surface(T[i][0], T[i][1], T[i][2]));
+    }
+    f3 ns = e_add(e_add(n0, n1), n2);
+    f3 nn = e_normalize(mk3(fd(ns.x, 3.0f), fd(ns.y, 3.0f), fd(ns.z, 3.0f)));
+    g.n = make_float4(nn.x, nn.y, nn.z, e_surface(a, b, c));
+    geom[p] = g;
+}
+
+int dz_precompute_geom(daisy_ctx *ctx) {
+    if (ctx->N == 0) return DAISY_OK;
+    k_patch_geom<<<(ctx->N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_vertices, ctx->d_normals, ctx->d_tri, ctx->N, ctx->d_geom);
+    DZ_CUDA(cudaGetLastError());
+    return DAISY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The 16 point-to-point terms of p2pFormfactor for origin patch o and destination patch d.
+// term(i,j) is symmetric under swapping the roles of the two patches bit for bit (negation and multiplication
+// commute exactly), so one evaluation yields F(o->d) = (sum_i sum_j term)/A_o and F(d->o) = (sum_j sum_i term)/A_d.
+template <int VARIANT>
+__device__ __forceinline__ void ff_pair(const PatchGeom &o, const PatchGeom &d, float &ff_od, float &ff_do) {
+    f3 no = xyz(o.n), nd = xyz(d.n);
+    float t[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            f3 v = e_sub(xyz(d.s[j]), xyz(o.s[i])); // dest.pos - orig.pos
+            float l2 = e_dot(v, v);
+            float len = fsq(l2);
+            float inv = fd(1.0f, len);
+            f3 nv = e_scale(v, inv);
+            float dot1 = e_dot(no, nv);
+            // normalize(orig.pos - dest.pos) is exactly -nv, and dot(n, -x) is exactly -dot(n, x)
+            float dot2 = -e_dot(nd, nv);
+            float term = 0.0f;
+            if (dot1 > 0.0f && dot2 > 0.0f) {
+                float surface = fm(o.s[i].w, d.s[j].w);
+                float len2 = fm(len, len); // powf(length, 2)
+                if (VARIANT == DAISY_FF_DEVICE) {
+                    // ((dot1*dot2) / (powf(length,2) * CUDART_PI)) * surface, CUDART_PI double   parallellism.cu:204
+                    double den = __dmul_rn((double)len2, PI_D);
+                    double q = __ddiv_rn((double)fm(dot1, dot2), den);
+                    term = __double2float_rn(__dmul_rn(q, (double)surface));
+                } else {
+                    // all-float host form with M_PIf                                          triangle_math.cpp:55
+                    term = fm(fd(fm(dot1, dot2), fm(len2, PI_F)), surface);
+                }
+            }
+            t[i][j] = term;
+        }
+    }
+    float s_od = 0.0f, s_do = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) s_od = fa(s_od, t[i][j]);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) s_do = fa(s_do, t[i][j]);
+    ff_od = fd(s_od, o.n.w);
+    ff_do = fd(s_do, d.n.w);
+}
+
+// dense unoccluded triplets, diagonal included (calculateRow, parallellism.cu:91-111)
+template <int VARIANT>
+__global__ void k_unoccluded(const PatchGeom *__restrict__ geom, int N, int row0, int nrows, daisy_tripl *__restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = row0 + blockIdx.y;
+    if (c >= N || r >= row0 + nrows) return;
+    PatchGeom o = geom[r], d = geom[c];
+    float f_od, f_do;
+    ff_pair<VARIANT>(o, d, f_od, f_do);
+    daisy_tripl t;
+    t.m_row = r; t.m_col = c;
+    t.m_value = (f_od > 0.0f) ? (double)f_od : 0.0; // NaN (coincident points) -> 0, as `formfactorRC > 0.0` does
+    out[(size_t)(r - row0) * N + c] = t;
+}
+
+int dz_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_tripl *d_out) {
+    if (nrows <= 0 || ctx->N == 0) return DAISY_OK;
+    dim3 grid((ctx->N + 127) / 128, nrows);
+    if (variant == DAISY_FF_DEVICE)
+        k_unoccluded<DAISY_FF_DEVICE><<<grid, 128, 0, ctx->stream>>>(ctx->d_geom, ctx->N, row0, nrows, d_out);
+    else
+        k_unoccluded<DAISY_FF_HOST><<<grid, 128, 0, ctx->stream>>>(ctx->d_geom, ctx->N, row0, nrows, d_out);
+    DZ_CUDA(cudaGetLastError());
+    return DAISY_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One visibility ray of the pair (lo -> hi), sample (u,v): restates OptixPrimeFunctionality.cpp:191-196 and the
+// hit test of :208, i.e. "closest hit over ALL triangles has t > 0 and is triangle hi".  Evaluated as an
+// occlusion query bounded by the hit on hi itself: the ray sees hi iff the watertight test accepts hi at t_hi and
+// no other triangle k is accepted with (t_k, k) < (t_hi, hi) lexicographically -- the same predicate, but the
+// traversal can stop at the first occluder and never looks beyond t_hi.
+__device__ __forceinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root,
+                                         const TriVerts &Tlo, const TriVerts &Thi, int lo, int hi, float u, float v) {
+    // uv2xyz: a + u*(b-a) + v*(c-a)                                                   triangle_math.cpp:3-9
+    f3 a0 = xyz(Tlo.a), a1 = xyz(Thi.a);
+    f3 org = e_add(e_add(a0, e_scale(e_sub(xyz(Tlo.b), a0), u)), e_scale(e_sub(xyz(Tlo.c), a0), v));
+    f3 dst = e_add(e_add(a1, e_scale(e_sub(xyz(Thi.b), a1), u)), e_scale(e_sub(xyz(Thi.c), a1), v));
+    f3 dir = e_normalize(e_sub(dst, org));      // optix::normalize(dest - origin)
+    f3 o = e_add(org, e_scale(dir, 0.000001f)); // origin + normalize(dest - origin)*0.000001f
+    WRay w = wray_setup(o, dir);
+    float thi, uu, vv;
+    if (!wray_tri(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv)) return false;
+    float tk;
+    // the origin patch itself takes part like any other triangle (lo < hi, so a tie on t hides hi)
+    if (wray_tri(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) return false;
+    f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    int stack[64];
+    int sp = 0;
+    int cur = root;
+    while (true) {
+        if (cur < 0) {
+            int k = ~cur;
+            if (k != lo && k != hi) {
+                TriVerts t = tv[k];
+                if (wray_tri(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return false;
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+            continue;
+        }
+        BvhNode nd = nodes[cur];
+        float tl, tr;
+        bool hl = ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, thi, tl);
+        bool hr = ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, thi, tr);
+        if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
+        else if (hl) cur = nd.d.x;
+        else if (hr) cur = nd.d.y;
+        else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return true;
+}
+
+struct FFParams {
+    const PatchGeom *geom;
+    const TriVerts *tv;
+    const BvhNode *nodes;
+    int root, N, S;
+    int row0, row1;      // rows this context owns
+    float *F;            // (row1-row0) x ldF, may be null (mask-only run)
+    int64_t ldF;
+    uint64_t *masks;     // optional (mrow1-mrow0) x N
+    int mrow0, mrow1;
+    int ntiles;          // tiles per side
+    int *job_counter;    // dynamic tile scheduler
+    unsigned long long *pair_counter;
+    int njobs;
+    const int2 *jobs;    // (row tile, col tile), col tile >= row tile
+};
+
+struct FFSmem {
+    PatchGeom gr[TILE], gc[TILE];
+    TriVerts tr[TILE], tc[TILE];
+    float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
+    float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
+    unsigned short list[TILE * TILE];
+    int nlist, next, job;
+};
+
+template <int VARIANT>
+__global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
+    extern __shared__ __align__(16) unsigned char ff_smem_raw[];
+    FFSmem &sm = *reinterpret_cast<FFSmem *>(ff_smem_raw);
+    PatchGeom *s_gr = sm.gr, *s_gc = sm.gc;
+    TriVerts *s_tr = sm.tr, *s_tc = sm.tc;
+    float(*s_rc)[TILE + 1] = sm.rc;
+    float(*s_cr)[TILE + 1] = sm.cr;
+    unsigned short *s_list = sm.list;
+    int &s_nlist = sm.nlist, &s_next = sm.next, &s_job = sm.job;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    while (true) {
+        if (tid == 0) s_job = atomicAdd(P.job_counter, 1);
+        __syncthreads();
+        int job = s_job;
+        if (job >= P.njobs) break;
+        int2 jt = P.jobs[job];
+        const int R0 = jt.x * TILE, C0 = jt.y * TILE;
+        const bool diag = (jt.x == jt.y);
+        if (tid == 0) { s_nlist = 0; s_next = 0; }
+        // stage the two patch groups (float4-granular copies: 5 + 3 float4 per patch)
+        for (int i = tid; i < TILE * 5; i += FF_THREADS) {
+            int p = i / 5, q = i - p * 5;
+            int gr = min(R0 + p, P.N - 1), gc = min(C0 + p, P.N - 1);
+            ((float4 *)&s_gr[p])[q] = ((const float4 *)&P.geom[gr])[q];
+            ((float4 *)&s_gc[p])[q] = ((const float4 *)&P.geom[gc])[q];
+        }
+        for (int i = tid; i < TILE * 3; i += FF_THREADS) {
+            int p = i / 3, q = i - p * 3;
+            int gr = min(R0 + p, P.N - 1), gc = min(C0 + p, P.N - 1);
+            ((float4 *)&s_tr[p])[q] = ((const float4 *)&P.tv[gr])[q];
+            ((float4 *)&s_tc[p])[q] = ((const float4 *)&P.tv[gc])[q];
+        }
+        __syncthreads();
+
+        // ---- phase 1: unoccluded form factors of every pair r < c of the tile; facing pairs go on the list
+        for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
+            int rl = idx >> 6, cl = idx & 63;
+            int r = R0 + rl, c = C0 + cl;
+            bool valid = (r < P.N) && (c < P.N) && (r < c) &&
+                         ((r >= P.row0 && r < P.row1) || (c >= P.row0 && c < P.row1));
+            float f_rc = 0.0f, f_cr = 0.0f;
+            bool trace = false;
+            if (valid) {
+                ff_pair<VARIANT>(s_gr[rl], s_gc[cl], f_rc, f_cr);
+                // calculateRow stores the value only when > 0 (parallellism.cu:101-107)
+                f_rc = (f_rc > 0.0f) ? f_rc : 0.0f;
+                f_cr = (f_cr > 0.0f) ? f_cr : 0.0f;
+                // cuda path: traced iff tripletlist[row*N+col].m_value > 0 (OptixPrimeFunctionality.cpp:190);
+                // per-pair path: every pair is traced and tested after the fact (:335-336) -- same matrix, since
+                // a zero unoccluded factor gives a zero entry either way
+                trace = f_rc > 0.0f;
+                if (!trace) f_cr = 0.0f;
+            }
+            s_rc[rl][cl] = f_rc;
+            s_cr[cl][rl] = f_cr;
+            unsigned m = __ballot_sync(0xffffffffu, trace);
+            if (m) {
+                int base = 0;
+                int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(&s_nlist, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (trace) s_list[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)idx;
+            }
+        }
+        __syncthreads();
+        const int nlist = s_nlist;
+        if (tid == 0 && nlist) atomicAdd(P.pair_counter, (unsigned long long)nlist);
+
+        // ---- phase 2: S visibility rays per listed pair; a warp claims 32 pairs at a time, lane = pair,
+        // all lanes trace sample i together (neighbouring pairs + same sample => coherent rays)
+        while (true) {
+            int q0 = 0;
+            if (lane == 0) q0 = atomicAdd(&s_next, 32);
+            q0 = __shfl_sync(0xffffffffu, q0, 0);
+            if (q0 >= nlist) break;
+            int q = q0 + lane;
+            if (q < nlist) {
+                int idx = s_list[q];
+                int rl = idx >> 6, cl = idx & 63;
+                int r = R0 + rl, c = C0 + cl;
+                const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
+                uint64_t mask = 0;
+                for (int i = 0; i < P.S; i++) {
+                    if (ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, r, c, c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << i);
+                }
+                // visibility = (#hits as float) / RAYS_PER_PATCH                 OptixPrimeFunctionality.cpp:206-211
+                float visibility = fd((float)__popcll(mask), (float)P.S);
+                float f_rc, f_cr;
+                if (VARIANT == DAISY_FF_DEVICE) {
+                    // Tripl(row, col, visibility * m_value): float*double in double; setFromTriplets casts to float
+                    f_rc = __double2float_rn(__dmul_rn((double)visibility, (double)s_rc[rl][cl]));
+                    f_cr = __double2float_rn(__dmul_rn((double)visibility, (double)s_cr[cl][rl]));
+                } else {
+                    // p2pFormfactor returns formfactor*visibility (float); mirrored entry by reciprocity      :165,:343
+                    f_rc = fm(s_rc[rl][cl], visibility);
+                    f_cr = (f_rc > 0.0f) ? fd(fm(s_gr[rl].n.w, f_rc), s_gc[cl].n.w) : 0.0f;
+                }
+                if (mask == 0) { f_rc = 0.0f; f_cr = 0.0f; }
+                s_rc[rl][cl] = f_rc;
+                s_cr[cl][rl] = f_cr;
+                if (P.masks) {
+                    if (r >= P.mrow0 && r < P.mrow1) P.masks[(size_t)(r - P.mrow0) * P.N + c] = mask;
+                    if (c >= P.mrow0 && c < P.mrow1) P.masks[(size_t)(c - P.mrow0) * P.N + r] = mask;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: coalesced tile stores.  Rows of s_rc are rows R0.. of F; rows of s_cr are rows C0.. of F.
+        if (P.F) {
+            for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
+                int a = idx >> 6, b = idx & 63;
+                if (diag) {
+                    int r = R0 + a, c = C0 + b;
+                    if (r < P.N && c < P.N && r >= P.row0 && r < P.row1) {
+                        float v = (a < b) ? s_rc[a][b] : ((a > b) ? s_cr[a][b] : 0.0f);
+                        P.F[(size_t)(r - P.row0) * P.ldF + c] = v;
+                    }
+                } else {
+                    int r = R0 + a, c = C0 + b;
+                    if (r < P.N && c < P.N && r >= P.row0 && r < P.row1) P.F[(size_t)(r - P.row0) * P.ldF + c] = s_rc[a][b];
+                    int r2 = C0 + a, c2 = R0 + b; // mirrored tile: row = column patch
+                    if (r2 < P.N && c2 < P.N && r2 >= P.row0 && r2 < P.row1) P.F[(size_t)(r2 - P.row0) * P.ldF + c2] = s_cr[a][b];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mrow0, int mrow1, bool write_F) {
+    const int N = ctx->N;
+    if (N == 0) return DAISY_OK;
+    cudaStream_t st = ctx->stream;
+    const int ntiles = (N + TILE - 1) / TILE;
+    // row range of interest: the context's rows when writing F, else the mask rows
+    int r0 = write_F ? ctx->row0 : mrow0, r1 = write_F ? ctx->row1 : mrow1;
+    if (r1 <= r0) return DAISY_OK;
+    int t0 = r0 / TILE, t1 = (r1 - 1) / TILE; // tiles overlapping the range
+    // jobs: upper-triangle tiles (R <= C) with R or C inside [t0, t1]
+    size_t njobs = 0;
+    for (int R = 0; R < ntiles; R++)
+        for (int C = R; C < ntiles; C++)
+            if ((R >= t0 && R <= t1) || (C >= t0 && C <= t1)) njobs++;
+    int2 *h_jobs = (int2 *)malloc(sizeof(int2) * (njobs ? njobs : 1));
+    if (!h_jobs) { daisy_set_error("out of host memory for the tile list"); return DAISY_E_NOMEM; }
+    size_t k = 0;
+    for (int R = 0; R < ntiles; R++)
+        for (int C = R; C < ntiles; C++)
+            if ((R >= t0 && R <= t1) || (C >= t0 && C <= t1)) h_jobs[k++] = make_int2(R, C);
+    int2 *d_jobs = nullptr;
+    int *d_counter = nullptr;
+    unsigned long long *d_pairs = nullptr;
+    DZ_CUDA(cudaMalloc(&d_jobs, sizeof(int2) * (njobs ? njobs : 1)));
+    DZ_CUDA(cudaMalloc(&d_counter, sizeof(int)));
+    DZ_CUDA(cudaMalloc(&d_pairs, sizeof(unsigned long long)));
+    DZ_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(int2) * njobs, cudaMemcpyHostToDevice, st));
+    DZ_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
+    DZ_CUDA(cudaMemsetAsync(d_pairs, 0, sizeof(unsigned long long), st));
+    FFParams P;
+    P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
+    P.row0 = r0; P.row1 = r1;
+    P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
+    P.masks = d_masks; P.mrow0 = mrow0; P.mrow1 = mrow1;
+    P.ntiles = ntiles; P.job_counter = d_counter; P.pair_counter = d_pairs; P.njobs = (int)njobs; P.jobs = d_jobs;
+    cudaEvent_t e0, e1;
+    DZ_CUDA(cudaEventCreate(&e0));
+    DZ_CUDA(cudaEventCreate(&e1));
+    int blocks_per_sm = 0;
+    const size_t smem = sizeof(FFSmem);
+    DZ_CUDA(cudaFuncSetAttribute(k_ff_tiles<DAISY_FF_DEVICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DZ_CUDA(cudaFuncSetAttribute(k_ff_tiles<DAISY_FF_HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (variant == DAISY_FF_DEVICE) DZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_ff_tiles<DAISY_FF_DEVICE>, FF_THREADS, smem));
+    else DZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_ff_tiles<DAISY_FF_HOST>, FF_THREADS, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int grid = ctx->num_sms * blocks_per_sm; // persistent CTAs, a multiple of the SM count
+    if ((size_t)grid > njobs) grid = (int)njobs;
+    DZ_CUDA(cudaEventRecord(e0, st));
+    if (variant == DAISY_FF_DEVICE) k_ff_tiles<DAISY_FF_DEVICE><<<grid, FF_THREADS, smem, st>>>(P);
+    else k_ff_tiles<DAISY_FF_HOST><<<grid, FF_THREADS, smem, st>>>(P);
+    DZ_CUDA(cudaGetLastError());
+    DZ_CUDA(cudaEventRecord(e1, st));
+    unsigned long long pairs = 0;
+    DZ_CUDA(cudaMemcpyAsync(&pairs, d_pairs, sizeof(pairs), cudaMemcpyDeviceToHost, st));
+    DZ_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (write_F) { ctx->ff_ms = ms; ctx->pairs_traced = (int64_t)pairs; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_jobs); cudaFree(d_counter); cudaFree(d_pairs);
+    free(h_jobs);
+    return DAISY_OK;
+}

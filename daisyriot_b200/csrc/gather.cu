@@ -1,0 +1,586 @@
+// gather.cu -- the radiosity / fluorescence gather pass: residual <- M (F residual); B += residual.
+//
+// Replaces the single-threaded Eigen loops of the reference's Lightning family ("visual studio/Lightning.h"):
+//   SpectralLightning::increment_light_fluorescent  :196-226  (K SpMVs + N KxK mat-vecs)
+//   RGBLightning::increment_lightpass               :342-349  (K=3, M = diag(rho))
+//   BWLightning::increment_lightpass                :419-424  (K=1, M = [1])
+//   converge_lightning / check_convergence          :145-151, :255-261, :336-340, :410-415
+//
+// F is dense FP32, row-major, resident in HBM; one pass streams it exactly once.  k_gather_partial is a persistent
+// kernel: a work item is (64-row block) x (column range); a warp owns R rows, lanes stride the columns with 128-bit
+// streaming loads, the K residual bands of the current 512-column tile are staged in shared memory by 1-D TMA bulk
+// copies (cp.async.bulk + mbarrier, double buffered) and every F element is used for K FMAs straight from
+// registers.  k_gather_epilogue sums the column-range partials, applies the per-material KxK matrix, accumulates
+// B, writes the new residual into the exchange block of this rank and totals the per-band residual sums.
+#include "daisy_common.cuh"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#define G_WARPS 8
+#define G_THREADS (G_WARPS * 32)
+#define G_TC 512 // residual tile width (columns)
+
+struct daisy_solver {
+    daisy_ctx *ctx = nullptr;
+    int K = 0, Kp = 0; // bands requested / bands the kernel is instantiated for
+    int nmat = 0;
+    int N = 0, n = 0, G = 1, rank = 0, nloc = 0, row0 = 0;
+    int64_t bstride = 0;   // floats per exchange block
+    int64_t sums_off = 0;  // float offset of the K doubles inside a block
+    float *d_res[2] = { nullptr, nullptr }; // exchange buffers (G blocks each)
+    int cur = 0;
+    float *d_B = nullptr;  // Kp x n   (band-major, local rows)
+    float *d_E = nullptr;  // exchange-layout copy of the emission (reset source)
+    float *d_M = nullptr;  // nmat x Kp x Kp column-major
+    int *d_mat = nullptr;  // local rows
+    float *d_partial = nullptr; // nsplit x nloc x Kp
+    double *d_cta_sums = nullptr;
+    unsigned int *d_done = nullptr;
+    int R = 8, nsplit = 1, grid = 148, colw = 0;
+    int numpasses = 0;
+    double last_ms = 0.0;
+    std::vector<double> sums;   // band sums of the current residual
+    bool sums_valid = true;
+    std::vector<double> e_sums; // band sums of the emission
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float4 ldg_stream(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+struct GatherParams {
+    const float *F; int64_t ldF;
+    int nloc;               // local rows
+    int ncols;              // padded column count G*n
+    int n;                  // rows per rank (block length)
+    const float *res;       // exchange buffer (read)
+    int64_t bstride;
+    float *partial;         // nsplit x nloc x K
+    int nsplit, colw;       // column range width per split (multiple of G_TC)
+    int nrb;                // row blocks
+};
+
+// stage the K bands of columns [j0, j0+w) of the exchange buffer into tile[k][0..w)
+template <int K>
+__device__ __forceinline__ void issue_tile(const GatherParams &P, float *tile, uint64_t *bar, int j0, int w) {
+    mbar_expect_tx(bar, (uint32_t)(K * w * 4));
+    int g = j0 / P.n, jl = j0 - g * P.n;
+    int w1 = min(w, P.n - jl); // part inside block g; the rest (if any) continues in block g+1
+#pragma unroll 1
+    for (int k = 0; k < K; k++) {
+        bulk_g2s(tile + k * G_TC, P.res + (size_t)g * P.bstride + (size_t)k * P.n + jl, (uint32_t)(w1 * 4), bar);
+        if (w1 < w) bulk_g2s(tile + k * G_TC + w1, P.res + (size_t)(g + 1) * P.bstride + (size_t)k * P.n, (uint32_t)((w - w1) * 4), bar);
+    }
+}
+
+template <int K, int R>
+__global__ void __launch_bounds__(G_THREADS, 1) k_gather_partial(GatherParams P) {
+    extern __shared__ __align__(128) unsigned char g_smem[];
+    float *tiles = reinterpret_cast<float *>(g_smem);                 // 2 x K x G_TC
+    uint64_t *bars = reinterpret_cast<uint64_t *>(g_smem + 2 * K * G_TC * sizeof(float));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t phase[2] = { 0, 0 };
+    const int nitems = P.nrb * P.nsplit;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int rb = item / P.nsplit, split = item - rb * P.nsplit;
+        const int c_begin = split * P.colw;
+        const int c_end = min(P.ncols, c_begin + P.colw);
+        const int ntile = (c_end - c_begin + G_TC - 1) / G_TC;
+        const int row_base = rb * (G_WARPS * R) + warp * R;
+        const float *Frow[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) Frow[r] = P.F + (size_t)min(row_base + r, P.nloc - 1) * P.ldF + c_begin + lane * 4;
+        float acc[R][K];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[r][k] = 0.0f;
+        if (tid == 0) {
+            issue_tile<K>(P, tiles, &bars[0], c_begin, min(G_TC, c_end - c_begin));
+            if (ntile > 1) issue_tile<K>(P, tiles + K * G_TC, &bars[1], c_begin + G_TC, min(G_TC, c_end - c_begin - G_TC));
+        }
+        const int nstep = (c_end - c_begin + 127) / 128;
+        float4 fcur[R], fnxt[R];
+        {
+            bool in = (lane * 4) < (c_end - c_begin);
+#pragma unroll
+            for (int r = 0; r < R; r++) fcur[r] = in ? ldg_stream(Frow[r]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int s = 0; s < nstep; s++) {
+            const int t = s >> 2, buf = t & 1;
+            if (s + 1 < nstep) {
+                bool in = ((s + 1) * 128 + lane * 4) < (c_end - c_begin);
+#pragma unroll
+                for (int r = 0; r < R; r++) fnxt[r] = in ? ldg_stream(Frow[r] + (size_t)(s + 1) * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if ((s & 3) == 0) { mbar_wait(&bars[buf], phase[buf]); phase[buf] ^= 1; }
+            const int col = (s & 3) * 128 + lane * 4; // tile-local column
+            if (t * G_TC + col < c_end - c_begin) {
+                const float *tile = tiles + buf * K * G_TC + col;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    float4 x = *reinterpret_cast<const float4 *>(tile + k * G_TC);
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        acc[r][k] = fmaf(fcur[r].x, x.x, acc[r][k]);
+                        acc[r][k] = fmaf(fcur[r].y, x.y, acc[r][k]);
+                        acc[r][k] = fmaf(fcur[r].z, x.z, acc[r][k]);
+                        acc[r][k] = fmaf(fcur[r].w, x.w, acc[r][k]);
+                    }
+                }
+            }
+            if ((s & 3) == 3 || s == nstep - 1) {
+                __syncthreads(); // every warp is done with tile t
+                if (tid == 0 && t + 2 < ntile) {
+                    int j0 = c_begin + (t + 2) * G_TC;
+                    issue_tile<K>(P, tiles + buf * K * G_TC, &bars[buf], j0, min(G_TC, c_end - j0));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) fcur[r] = fnxt[r];
+        }
+        // lane reduction (fixed xor tree => deterministic), lane 0 stores the column-range partial
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                float v = acc[r][k];
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                acc[r][k] = v;
+            }
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                int row = row_base + r;
+                if (row < P.nloc) {
+                    float *dst = P.partial + ((size_t)split * P.nloc + row) * K;
+#pragma unroll
+                    for (int k = 0; k < K; k++) dst[k] = acc[r][k];
+                }
+            }
+        }
+    }
+}
+
+struct EpiParams {
+    const float *partial; int nsplit, nloc, n;
+    const float *M; const int *mat;
+    float *res_out_block; // this rank's block of the next exchange buffer: K x n floats
+    float *B;             // K x n
+    double *cta_sums;     // gridDim x K
+    double *block_sums;   // K doubles in the tail of this rank's block
+    unsigned int *done;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) k_gather_epilogue(EpiParams P) {
+    __shared__ double s_sum[8][K];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double loc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) loc[k] = 0.0;
+    for (int row = blockIdx.x * blockDim.x + tid; row < P.nloc; row += gridDim.x * blockDim.x) {
+        float b[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) b[k] = 0.0f;
+        for (int s = 0; s < P.nsplit; s++) {
+            const float *src = P.partial + ((size_t)s * P.nloc + row) * K;
+#pragma unroll
+            for (int k = 0; k < K; k++) b[k] += src[k];
+        }
+        const float *Mp = P.M + (size_t)P.mat[row] * K * K;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            // result = reflectionmatrix[i] * patchrowvec  (column-major K x K)            Lightning.h:212
+            float y = 0.0f;
+#pragma unroll
+            for (int j = 0; j < K; j++) y = fmaf(Mp[j * K + k], b[j], y);
+            P.res_out_block[(size_t)k * P.n + row] = y;                          // residualvector[j][i] = result[j]
+            P.B[(size_t)k * P.n + row] = P.B[(size_t)k * P.n + row] + y;         // lightningvalues += residual   :221-223
+            loc[k] += (double)y;
+        }
+    }
+    // deterministic totals: lanes -> warps -> CTA -> (last CTA) grid, always in index order
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double v = loc[k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_sum[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < K) {
+        double v = 0.0;
+        for (int w = 0; w < 8; w++) v += s_sum[w][tid];
+        P.cta_sums[(size_t)blockIdx.x * K + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(P.done, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (tid < K) {
+            double v = 0.0;
+            volatile const double *cs = P.cta_sums;
+            for (unsigned b = 0; b < gridDim.x; b++) v += cs[(size_t)b * K + tid];
+            P.block_sums[tid] = v;
+        }
+        if (tid == 0) *P.done = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <int K, int R>
+static int launch_partial(daisy_solver *s, const GatherParams &P) {
+    size_t smem = 2 * K * G_TC * sizeof(float) + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        DZ_CUDA(cudaFuncSetAttribute(k_gather_partial<K, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k_gather_partial<K, R><<<s->grid, G_THREADS, smem, s->ctx->stream>>>(P);
+    DZ_CUDA(cudaGetLastError());
+    return DAISY_OK;
+}
+
+template <int K>
+static int launch_pass_K(daisy_solver *s) {
+    daisy_ctx *c = s->ctx;
+    GatherParams P;
+    P.F = c->d_F; P.ldF = c->ldF; P.nloc = s->nloc; P.ncols = s->G * s->n; P.n = s->n;
+    P.res = s->d_res[s->cur]; P.bstride = s->bstride; P.partial = s->d_partial;
+    P.nsplit = s->nsplit; P.colw = s->colw; P.nrb = (s->nloc + G_WARPS * s->R - 1) / (G_WARPS * s->R);
+    int rc;
+    if constexpr (K <= 9) {
+        rc = (s->R == 8) ? launch_partial<K, 8>(s, P) : launch_partial<K, 4>(s, P);
+    } else {
+        rc = (s->R == 4) ? launch_partial<K, 4>(s, P) : launch_partial<K, 2>(s, P);
+    }
+    if (rc) return rc;
+    EpiParams E;
+    float *next = s->d_res[s->cur ^ 1] + (size_t)s->rank * s->bstride;
+    E.partial = s->d_partial; E.nsplit = s->nsplit; E.nloc = s->nloc; E.n = s->n;
+    E.M = s->d_M; E.mat = s->d_mat; E.res_out_block = next; E.B = s->d_B;
+    E.cta_sums = s->d_cta_sums; E.block_sums = reinterpret_cast<double *>(next + s->sums_off); E.done = s->d_done;
+    int egrid = (s->nloc + 255) / 256;
+    if (egrid > 148) egrid = 148;
+    if (egrid < 1) egrid = 1;
+    k_gather_epilogue<K><<<egrid, 256, 0, c->stream>>>(E);
+    DZ_CUDA(cudaGetLastError());
+    return DAISY_OK;
+}
+
+static int launch_pass(daisy_solver *s) {
+    switch (s->Kp) {
+    case 1: return launch_pass_K<1>(s);
+    case 3: return launch_pass_K<3>(s);
+    case 9: return launch_pass_K<9>(s);
+    case 16: return launch_pass_K<16>(s);
+    case 32: return launch_pass_K<32>(s);
+    }
+    daisy_set_error("unsupported padded band count %d", s->Kp);
+    return DAISY_E_INVALID;
+}
+
+// choose rows-per-warp and the column split so that (row blocks x splits) fills the persistent grid evenly
+static void plan(daisy_solver *s) {
+    int sms = s->ctx->num_sms;
+    s->grid = sms;
+    int Rs[2];
+    if (s->Kp <= 9) { Rs[0] = 8; Rs[1] = 4; } else { Rs[0] = 2; Rs[1] = 4; }
+    int ncols = s->G * s->n;
+    int maxsplit = (ncols + 4 * G_TC - 1) / (4 * G_TC); // keep at least 2048 columns per item
+    if (maxsplit < 1) maxsplit = 1;
+    if (maxsplit > 32) maxsplit = 32;
+    double best = -1.0;
+    for (int ri = 0; ri < 2; ri++) {
+        int R = Rs[ri];
+        int nrb = (s->nloc + G_WARPS * R - 1) / (G_WARPS * R);
+        for (int sp = 1; sp <= maxsplit; sp++) {
+            long items = (long)nrb * sp;
+            long rounds = (items + sms - 1) / sms;
+            double eff = (double)items / (double)(rounds * sms);
+            eff -= 0.004 * (sp - 1) + (ri == 1 ? 0.02 : 0.0); // prefer fewer splits and the first R on ties
+            if (eff > best) { best = eff; s->R = R; s->nsplit = sp; }
+        }
+    }
+    int colw = (ncols + s->nsplit - 1) / s->nsplit;
+    s->colw = ((colw + G_TC - 1) / G_TC) * G_TC;
+    s->nsplit = (ncols + s->colw - 1) / s->colw;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int padded_K(int K) { return K <= 1 ? 1 : K <= 3 ? 3 : K <= 9 ? 9 : K <= 16 ? 16 : 32; }
+
+static void free_solver(daisy_solver *s) {
+    if (!s) return;
+    cudaFree(s->d_res[0]); cudaFree(s->d_res[1]); cudaFree(s->d_B); cudaFree(s->d_E); cudaFree(s->d_M); cudaFree(s->d_mat);
+    cudaFree(s->d_partial); cudaFree(s->d_cta_sums); cudaFree(s->d_done);
+    if (s->e0) cudaEventDestroy(s->e0);
+    if (s->e1) cudaEventDestroy(s->e1);
+    delete s;
+}
+
+// host (K x N band-major) -> exchange layout (G blocks of [Kp x n] + tail)
+static void to_exchange(const daisy_solver *s, const float *src, std::vector<float> &dst) {
+    dst.assign((size_t)s->G * s->bstride, 0.0f);
+    for (int k = 0; k < s->K; k++)
+        for (int p = 0; p < s->N; p++) {
+            int g = p / s->n, jl = p - g * s->n;
+            dst[(size_t)g * s->bstride + (size_t)k * s->n + jl] = src[(size_t)k * s->N + p];
+        }
+}
+
+static int compute_sums_from_host(daisy_solver *s, const float *res /* K x N */) {
+    // band sums of a residual supplied by the host (reset / write): same quantity the kernels total on device
+    s->sums.assign(s->K, 0.0);
+    for (int k = 0; k < s->K; k++) {
+        double v = 0.0;
+        for (int p = 0; p < s->N; p++) v += (double)res[(size_t)k * s->N + p];
+        s->sums[k] = v;
+    }
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const float *M, int nmat, const int32_t *mat_idx,
+                                   daisy_solver **out) {
+    DZ_REQUIRE(ctx && out && E && M && mat_idx, DAISY_E_INVALID, "daisy_solver_create: null argument");
+    DZ_REQUIRE(K >= 1 && K <= DAISY_MAX_BANDS, DAISY_E_INVALID, "daisy_solver_create: K must be in [1,32]");
+    DZ_REQUIRE(nmat >= 1, DAISY_E_INVALID, "daisy_solver_create: need at least one material");
+    DZ_REQUIRE(ctx->have_F, DAISY_E_STATE, "daisy_solver_create: build or load the form factors first");
+    DZ_REQUIRE(ctx->N > 0, DAISY_E_INVALID, "daisy_solver_create: empty mesh");
+    for (int p = 0; p < ctx->N; p++)
+        DZ_REQUIRE(mat_idx[p] >= 0 && mat_idx[p] < nmat, DAISY_E_INVALID, "daisy_solver_create: material index out of range");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    daisy_solver *s = new daisy_solver();
+    s->ctx = ctx; s->K = K; s->Kp = padded_K(K); s->nmat = nmat;
+    s->N = ctx->N; s->n = ctx->rows_per_rank; s->G = ctx->nranks; s->rank = ctx->rank;
+    s->row0 = ctx->row0; s->nloc = ctx->row1 - ctx->row0;
+    int64_t body = (int64_t)s->Kp * s->n;
+    s->sums_off = body;
+    s->bstride = ((body + 2 * s->Kp + 3) / 4) * 4; // K doubles = 2K floats, block padded to 16 B
+    plan(s);
+    size_t exb = sizeof(float) * (size_t)s->G * s->bstride;
+    int rc = DAISY_OK;
+#define SC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { daisy_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); free_solver(s); return DAISY_E_CUDA; } } while (0)
+    SC(cudaMalloc(&s->d_res[0], exb));
+    SC(cudaMalloc(&s->d_res[1], exb));
+    SC(cudaMalloc(&s->d_E, exb));
+    SC(cudaMalloc(&s->d_B, sizeof(float) * (size_t)s->Kp * s->n));
+    SC(cudaMalloc(&s->d_M, sizeof(float) * (size_t)nmat * s->Kp * s->Kp));
+    SC(cudaMalloc(&s->d_mat, sizeof(int) * (size_t)(s->nloc > 0 ? s->nloc : 1)));
+    SC(cudaMalloc(&s->d_partial, sizeof(float) * (size_t)s->nsplit * (s->nloc > 0 ? s->nloc : 1) * s->Kp));
+    SC(cudaMalloc(&s->d_cta_sums, sizeof(double) * 148 * s->Kp));
+    SC(cudaMalloc(&s->d_done, sizeof(unsigned int)));
+    SC(cudaMemset(s->d_done, 0, sizeof(unsigned int)));
+    SC(cudaMemset(s->d_res[0], 0, exb));
+    SC(cudaMemset(s->d_res[1], 0, exb));
+    SC(cudaEventCreate(&s->e0));
+    SC(cudaEventCreate(&s->e1));
+    {
+        std::vector<float> ex;
+        to_exchange(s, E, ex);
+        SC(cudaMemcpy(s->d_E, ex.data(), exb, cudaMemcpyHostToDevice));
+        // M padded to Kp x Kp (extra bands are inert: zero rows/columns)
+        std::vector<float> Mp((size_t)nmat * s->Kp * s->Kp, 0.0f);
+        for (int m = 0; m < nmat; m++)
+            for (int j = 0; j < K; j++)
+                for (int i = 0; i < K; i++) Mp[((size_t)m * s->Kp + j) * s->Kp + i] = M[((size_t)m * K + j) * K + i];
+        SC(cudaMemcpy(s->d_M, Mp.data(), sizeof(float) * Mp.size(), cudaMemcpyHostToDevice));
+        if (s->nloc > 0) SC(cudaMemcpy(s->d_mat, mat_idx + s->row0, sizeof(int) * (size_t)s->nloc, cudaMemcpyHostToDevice));
+    }
+#undef SC
+    compute_sums_from_host(s, E);
+    s->e_sums = s->sums;
+    *out = s;
+    rc = daisy_solver_reset(s);
+    if (rc) { free_solver(s); *out = nullptr; }
+    return rc;
+}
+
+extern "C" void daisy_solver_destroy(daisy_solver *s) {
+    if (s && s->ctx) cudaSetDevice(s->ctx->device);
+    free_solver(s);
+}
+
+extern "C" int daisy_solver_reset(daisy_solver *s) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_reset: null solver");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    size_t exb = sizeof(float) * (size_t)s->G * s->bstride;
+    // residualvector = emission; lightningvalues = emission                                 Lightning.h:159-165
+    s->cur = 0;
+    DZ_CUDA(cudaMemcpyAsync(s->d_res[0], s->d_E, exb, cudaMemcpyDeviceToDevice, st));
+    DZ_CUDA(cudaMemcpyAsync(s->d_B, s->d_E + (size_t)s->rank * s->bstride, sizeof(float) * (size_t)s->Kp * s->n, cudaMemcpyDeviceToDevice, st));
+    DZ_CUDA(cudaStreamSynchronize(st));
+    s->numpasses = 0;
+    s->sums = s->e_sums; // band sums of E, totalled once at create
+    s->sums_valid = true;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_step_local(daisy_solver *s) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_step_local: null solver");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    DZ_CUDA(cudaEventRecord(s->e0, st));
+    int rc = launch_pass(s);
+    if (rc) return rc;
+    DZ_CUDA(cudaEventRecord(s->e1, st));
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_exchange_info(daisy_solver *s, void **d_next_buffer, int64_t *block_bytes, int64_t *total_bytes) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_exchange_info: null solver");
+    if (d_next_buffer) *d_next_buffer = s->d_res[s->cur ^ 1];
+    if (block_bytes) *block_bytes = (int64_t)sizeof(float) * s->bstride;
+    if (total_bytes) *total_bytes = (int64_t)sizeof(float) * s->bstride * s->G;
+    return DAISY_OK;
+}
+
+static int fetch_sums(daisy_solver *s) {
+    // per-rank partial band sums sit in the tail of every block of the current buffer
+    cudaStream_t st = s->ctx->stream;
+    std::vector<double> tails((size_t)s->G * s->Kp);
+    for (int g = 0; g < s->G; g++)
+        DZ_CUDA(cudaMemcpyAsync(&tails[(size_t)g * s->Kp], s->d_res[s->cur] + (size_t)g * s->bstride + s->sums_off,
+                                sizeof(double) * s->Kp, cudaMemcpyDeviceToHost, st));
+    DZ_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->e0, s->e1) == cudaSuccess) s->last_ms = ms;
+    s->sums.assign(s->K, 0.0);
+    for (int k = 0; k < s->K; k++) {
+        double v = 0.0;
+        for (int g = 0; g < s->G; g++) v += tails[(size_t)g * s->Kp + k];
+        s->sums[k] = v;
+    }
+    s->sums_valid = true;
+    return DAISY_OK;
+}
+
+// band_sums == NULL: nothing is read back and the call does not wait for the device (back-to-back passes);
+// the sums are fetched lazily by daisy_solver_band_sums / daisy_solver_converge.
+extern "C" int daisy_solver_step_finish(daisy_solver *s, double *band_sums) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_step_finish: null solver");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    s->cur ^= 1;
+    s->numpasses++;
+    s->sums_valid = false;
+    if (!band_sums) return DAISY_OK;
+    int rc = fetch_sums(s);
+    if (rc) return rc;
+    memcpy(band_sums, s->sums.data(), sizeof(double) * s->K);
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_step(daisy_solver *s, double *band_sums) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_step: null solver");
+    DZ_REQUIRE(s->G == 1, DAISY_E_STATE, "daisy_solver_step: partitioned solver needs step_local / exchange / step_finish");
+    int rc = daisy_solver_step_local(s);
+    if (rc) return rc;
+    return daisy_solver_step_finish(s, band_sums);
+}
+
+static bool unconverged(const daisy_solver *s, double threshold, int per_band) {
+    if (per_band) {
+        for (int k = 0; k < s->K; k++) if (s->sums[k] > threshold) return true;
+        return false;
+    }
+    double tot = 0.0;
+    for (int k = 0; k < s->K; k++) tot += s->sums[k];
+    return tot > threshold;
+}
+
+extern "C" int daisy_solver_converge(daisy_solver *s, double threshold, int per_band, int max_passes, int *passes_out) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_converge: null solver");
+    DZ_REQUIRE(s->G == 1, DAISY_E_STATE, "daisy_solver_converge: partitioned solver is driven by the host exchange loop");
+    int done = 0;
+    std::vector<double> tmp(s->K);
+    if (!s->sums_valid) { int rc = fetch_sums(s); if (rc) return rc; }
+    while (unconverged(s, threshold, per_band) && (max_passes <= 0 || done < max_passes)) {
+        int rc = daisy_solver_step(s, tmp.data());
+        if (rc) return rc;
+        done++;
+    }
+    if (passes_out) *passes_out = s->numpasses;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_numpasses(daisy_solver *s) { return s ? s->numpasses : DAISY_E_INVALID; }
+
+extern "C" int daisy_solver_band_sums(daisy_solver *s, double *band_sums) {
+    DZ_REQUIRE(s && band_sums, DAISY_E_INVALID, "daisy_solver_band_sums: null argument");
+    if (!s->sums_valid) { DZ_CUDA(cudaSetDevice(s->ctx->device)); int rc = fetch_sums(s); if (rc) return rc; }
+    memcpy(band_sums, s->sums.data(), sizeof(double) * s->K);
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_read(daisy_solver *s, float *B, float *residual) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_read: null solver");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    DZ_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    // local rows only: out[k*nloc + pl]
+    if (B)
+        DZ_CUDA(cudaMemcpy2D(B, sizeof(float) * s->nloc, s->d_B, sizeof(float) * s->n, sizeof(float) * s->nloc, s->K, cudaMemcpyDeviceToHost));
+    if (residual)
+        DZ_CUDA(cudaMemcpy2D(residual, sizeof(float) * s->nloc, s->d_res[s->cur] + (size_t)s->rank * s->bstride, sizeof(float) * s->n,
+                             sizeof(float) * s->nloc, s->K, cudaMemcpyDeviceToHost));
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_write(daisy_solver *s, const float *B, const float *residual) {
+    DZ_REQUIRE(s && B && residual, DAISY_E_INVALID, "daisy_solver_write: null argument");
+    DZ_REQUIRE(s->G == 1, DAISY_E_STATE, "daisy_solver_write: single-GPU solvers only");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    DZ_CUDA(cudaMemcpy2DAsync(s->d_B, sizeof(float) * s->n, B, sizeof(float) * s->N, sizeof(float) * s->N, s->K, cudaMemcpyHostToDevice, st));
+    DZ_CUDA(cudaMemcpy2DAsync(s->d_res[s->cur], sizeof(float) * s->n, residual, sizeof(float) * s->N, sizeof(float) * s->N, s->K,
+                              cudaMemcpyHostToDevice, st));
+    DZ_CUDA(cudaStreamSynchronize(st));
+    compute_sums_from_host(s, residual);
+    s->sums_valid = true;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_last_step_ms(daisy_solver *s, double *ms) {
+    DZ_REQUIRE(s && ms, DAISY_E_INVALID, "daisy_solver_last_step_ms: null argument");
+    *ms = s->last_ms;
+    return DAISY_OK;
+}

@@ -1,0 +1,138 @@
+/*
+ * daisy_b200.h -- C-ABI of the B200-native form-factor + radiosity-gather path.
+ *
+ * Drop-in boundary for DaisyRiot's two data-parallel hot paths.  Plain pointers and sizes only; every
+ * entry point is blocking (the reference is single-threaded and synchronous, main.cpp:97-113), returns 0 on
+ * success or a negative DAISY_E_* code, and never throws.  daisy_last_error() gives the message of the last
+ * failure on the calling thread.  Host arrays are copied on entry (the reference's OptiX model likewise
+ * snapshots its host buffers at update(), OptixPrimeFunctionality.cpp:38-47); the caller keeps ownership.
+ *
+ * "VS/" = reference directory "visual studio/".  Layouts accepted verbatim from the reference:
+ *   glm::vec3 = 3 packed floats; vertex::TriangleIndex = 6 int32 {v0,v1,v2,n0,n1,n2} (VS/Vertex.h:11-14);
+ *   ray = 6 floats origin,direction (RTP_BUFFER_FORMAT_RAY_ORIGIN_DIRECTION, VS/OptixPrimeFunctionality.cpp:68);
+ *   daisy_hit = optix_functionality::Hit (VS/optix_functionality.h:10-14); UV = 2 floats (VS/Defines.h:3-6);
+ *   daisy_tripl = parallellism::Tripl {int,int,double} (VS/parallellism.cuh:30-33);
+ *   band vectors = K contiguous float[N] (std::vector<Eigen::VectorXf>, VS/Lightning.h:107-109);
+ *   material matrices = K x K column-major floats (Eigen::MatrixXf, VS/Material.h:17).
+ */
+#ifndef DAISY_B200_H
+#define DAISY_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAISY_OK 0
+#define DAISY_E_INVALID (-1) /* bad argument */
+#define DAISY_E_CUDA (-2)    /* CUDA runtime error (message in daisy_last_error) */
+#define DAISY_E_STATE (-3)   /* call out of order (e.g. solver before form factors) */
+#define DAISY_E_NOMEM (-4)
+
+#define DAISY_MAX_SAMPLES 64 /* visibility masks are 64-bit; the reference uses RAYS_PER_PATCH = 50 */
+#define DAISY_MAX_BANDS 32
+
+typedef struct daisy_ctx daisy_ctx;       /* ~ OptixPrimeFunctionality (+ the RadMat it fills) */
+typedef struct daisy_solver daisy_solver; /* ~ Lightning / SpectralLightning / RGBLightning / BWLightning */
+
+typedef struct { float t; int32_t triangleId; float u, v; } daisy_hit;
+typedef struct { int32_t m_row, m_col; double m_value; } daisy_tripl;
+
+/* form-factor arithmetic variant */
+#define DAISY_FF_DEVICE 0 /* cuda_on=true : calculateRow, double pi          (VS/parallellism.cu:91-207) */
+#define DAISY_FF_HOST 1   /* cuda_on=false: per-pair loop, float pi + reciprocity (VS/OptixPrimeFunctionality.cpp:311-366) */
+
+const char *daisy_last_error(void);
+int daisy_version(void);
+int daisy_device_count(void);
+
+/* ---- context: mesh upload + LBVH build + sample pattern ------------------------------------------------
+ * replaces OptixPrimeFunctionality::OptixPrimeFunctionality(MeshS&)         VS/OptixPrimeFunctionality.cpp:36-64
+ * (Context::create, setTriangles(host idx, host vtx), model->update -> here: Morton LBVH on `device`). */
+int daisy_ctx_create(const float *vertices, int nv, const float *normals, int nn, const int32_t *tri_idx, int ntri,
+                     int device, daisy_ctx **out);
+void daisy_ctx_destroy(daisy_ctx *ctx);
+/* the `rands` pattern (VS/OptixPrimeFunctionality.cpp:55-63); uv = S x {u,v}, 1 <= S <= 64.  The reference
+ * draws it from rand() seeded by wall-clock time, so the drop-in takes it as an input. */
+int daisy_ctx_set_samples(daisy_ctx *ctx, const float *uv, int S);
+/* multi-GPU (one process per GPU): this context builds and owns the row block `rank` of `nranks` equal blocks of
+ * rows_per_rank = ceil(N/nranks) rounded up to a multiple of 4 (default rank 0 of 1 = all rows).  Must be called
+ * before daisy_formfactors_build. */
+int daisy_ctx_set_partition(daisy_ctx *ctx, int rank, int nranks);
+int daisy_ctx_row_range(daisy_ctx *ctx, int *row0, int *row1, int *rows_per_rank);
+/* optional: run kernels on this cudaStream_t (default: the legacy default stream) */
+int daisy_ctx_set_stream(daisy_ctx *ctx, void *cuda_stream);
+
+/* ---- closest hit ----------------------------------------------------------------------------------------
+ * replaces OptixPrimeFunctionality::optixQuery(int, vector<float3>&, vector<Hit>&)   VS/OptixPrimeFunctionality.cpp:66-81
+ * RTP_QUERY_TYPE_CLOSEST, host ray buffer in, host hit buffer out; miss => t = -1, triangleId = -1. */
+int daisy_query_closest(daisy_ctx *ctx, int n, const float *rays6, daisy_hit *hits);
+/* same with device pointers (no copies) */
+int daisy_query_closest_device(daisy_ctx *ctx, int n, const float *d_rays6, daisy_hit *d_hits);
+
+/* ---- form factors -----------------------------------------------------------------------------------------
+ * replaces parallellism::runCalculateRadiosityMatrix(SimpleMesh&)                    VS/parallellism.cu:4-89
+ * dense unoccluded triplets of rows [row0,row0+nrows): out[(r-row0)*N + c] = {r, c, F_unoccluded(r->c)} */
+int daisy_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_tripl *out);
+/* replaces cudaCalculateRadiosityMatrix(SpMat&, MeshS&) (variant DEVICE)            VS/OptixPrimeFunctionality.cpp:6-34
+ *      and calculateRadiosityMatrix(SpMat&, MeshS&)     (variant HOST)              VS/OptixPrimeFunctionality.cpp:311-366
+ * i.e. runCalculateRadiosityMatrix + calculateAllVisibility (:169-242) fused: unoccluded 4x4 rule, S visibility
+ * rays per mutually facing pair, RadMat(row,col) = visibility * F(row->col).  The matrix stays resident on the
+ * device as dense FP32 rows [row0,row1) x N (leading dimension daisy_formfactors_ld). */
+int daisy_formfactors_build(daisy_ctx *ctx, int variant);
+int daisy_formfactors_ld(daisy_ctx *ctx, int64_t *ld_out);
+/* copy rows to host: out[(r-row0)*N + c], rows must lie inside the context's row range */
+int daisy_formfactors_read_rows(daisy_ctx *ctx, int row0, int nrows, float *out);
+/* refill an Eigen::SparseMatrix<float> (column-major CSC, sorted inner indices, as setFromTriplets leaves it,
+ * VS/OptixPrimeFunctionality.cpp:25).  Call with values==NULL to get nnz first.  Single-GPU contexts only. */
+int daisy_formfactors_to_csc(daisy_ctx *ctx, int64_t *nnz, float *values, int32_t *inner_idx, int32_t *outer_ptr);
+/* load a dense matrix instead of building it (the reference's on-disk cache path, VS/Lightning.h:84-96) */
+int daisy_formfactors_write_rows(daisy_ctx *ctx, int row0, int nrows, const float *in);
+/* parity aid: visibility hit masks of rows [row0,row0+nrows): out[(r-row0)*N + c], bit i = sample i of the pair
+ * (min(r,c) -> max(r,c)) saw its destination (the test at VS/OptixPrimeFunctionality.cpp:208); 0 if not traced. */
+int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int nrows, uint64_t *out);
+/* what the last daisy_formfactors_build did: pairs traced (unique, this context), rays, and device milliseconds
+ * of the LBVH build and of the fused form-factor/visibility kernel */
+int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *rays, double *lbvh_ms, double *ff_ms);
+
+/* ---- radiosity / fluorescence gather ------------------------------------------------------------------------
+ * replaces the Lightning family (VS/Lightning.h): residual <- M (F residual); B += residual
+ *   K=1, M=[1]            : BWLightning       (:386-443)
+ *   K=3, M=diag(rho_rgb)  : RGBLightning      (:298-384)
+ *   K=#wavelengths, full M: SpectralLightning (:99-295, hot loop :196-226)
+ * E: K x N band-major emission (already scaled by emission_value, as set_sampled_emission does, :263-273).
+ * M: nmat x K x K column-major; mat_idx: N material ids (MeshS::materialIndexPerTriangle). */
+int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const float *M, int nmat, const int32_t *mat_idx,
+                        daisy_solver **out);
+void daisy_solver_destroy(daisy_solver *s);
+int daisy_solver_reset(daisy_solver *s);                     /* reset(): residual = B = E             (:159-165) */
+/* one pass (increment_lightpass / increment_light_fluorescent); band_sums[K] = sum over patches of the new
+ * residual per band (the quantity check_convergence / .sum() test, :255-261), may be NULL */
+int daisy_solver_step(daisy_solver *s, double *band_sums);
+/* converge_lightning(): while (criterion(residual) > threshold) step.  per_band=0: sum over all bands > threshold
+ * (spectral, threshold 200, :145-151); per_band=1: any band sum > threshold (RGB/BW, 1e-4, :336-340, :410-415). */
+int daisy_solver_converge(daisy_solver *s, double threshold, int per_band, int max_passes, int *passes_out);
+int daisy_solver_numpasses(daisy_solver *s);
+/* per-band sums of the current residual (what the convergence test looks at), K doubles */
+int daisy_solver_band_sums(daisy_solver *s, double *band_sums);
+/* lightningvalues and residualvector, K x N band-major (rows of this context's range; full N when single GPU) */
+int daisy_solver_read(daisy_solver *s, float *B, float *residual);
+/* overwrite the current residual and B from host (K x N band-major) -- used by the end-to-end benchmark */
+int daisy_solver_write(daisy_solver *s, const float *B, const float *residual);
+
+/* ---- multi-GPU plumbing (one process per GPU; the host does the exchange with NCCL / torch.distributed) -----
+ * With daisy_ctx_set_partition(rank, nranks) the residual lives in an exchange buffer of `nranks` equal blocks,
+ * block g = [K x rows_per_rank floats][K doubles of partial band sums, padded to 16 B], so that one in-place
+ * all-gather of `block_bytes` per rank completes a pass.
+ *   daisy_solver_step_local : gather kernel over the local rows, writes block `rank` of the *next* buffer
+ *   (host: all_gather in place on next_buffer)
+ *   daisy_solver_step_finish: swap buffers, total the per-rank band sums */
+int daisy_solver_step_local(daisy_solver *s);
+int daisy_solver_exchange_info(daisy_solver *s, void **d_next_buffer, int64_t *block_bytes, int64_t *total_bytes);
+int daisy_solver_step_finish(daisy_solver *s, double *band_sums);
+/* timing of the last step: device milliseconds of the gather kernel (CUDA events on the context's stream) */
+int daisy_solver_last_step_ms(daisy_solver *s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
