@@ -300,9 +300,10 @@ extern "C" int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int
     return rc;
 }
 
-extern "C" int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *rays, double *lbvh_ms, double *ff_ms) {
+extern "C" int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *pairs_owned, int64_t *rays, double *lbvh_ms, double *ff_ms) {
     DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_formfactors_stats: null context");
     if (pairs_traced) *pairs_traced = ctx->pairs_traced;
+    if (pairs_owned) *pairs_owned = ctx->pairs_owned;
     if (rays) *rays = ctx->pairs_traced * (int64_t)ctx->S;
     if (lbvh_ms) *lbvh_ms = ctx->lbvh_ms;
     if (ff_ms) *ff_ms = ctx->ff_ms;

@@ -154,7 +154,7 @@ struct daisy_ctx {
     float *d_F = nullptr; // (row1-row0) x ldF
     int64_t ldF = 0;
     bool have_F = false;
-    int64_t pairs_traced = 0;
+    int64_t pairs_traced = 0, pairs_owned = 0;
     double ff_ms = 0.0;
     int num_sms = 148;
 };

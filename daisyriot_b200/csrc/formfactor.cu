@@ -201,7 +201,7 @@ struct FFParams {
     int mrow0, mrow1;
     int ntiles;          // tiles per side
     int *job_counter;    // dynamic tile scheduler
-    unsigned long long *pair_counter;
+    unsigned long long *pair_counter; // [0] pairs traced by this context, [1] of those, pairs whose lower index it owns
     int njobs;
     const int2 *jobs;    // (row tile, col tile), col tile >= row tile
 };
@@ -212,7 +212,7 @@ struct FFSmem {
     float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
     float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
     unsigned short list[TILE * TILE];
-    int nlist, next, job;
+    int nlist, next, job, nown;
 };
 
 template <int VARIANT>
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
     float(*s_rc)[TILE + 1] = sm.rc;
     float(*s_cr)[TILE + 1] = sm.cr;
     unsigned short *s_list = sm.list;
-    int &s_nlist = sm.nlist, &s_next = sm.next, &s_job = sm.job;
+    int &s_nlist = sm.nlist, &s_next = sm.next, &s_job = sm.job, &s_nown = sm.nown;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
         int2 jt = P.jobs[job];
         const int R0 = jt.x * TILE, C0 = jt.y * TILE;
         const bool diag = (jt.x == jt.y);
-        if (tid == 0) { s_nlist = 0; s_next = 0; }
+        if (tid == 0) { s_nlist = 0; s_next = 0; s_nown = 0; }
         // stage the two patch groups (float4-granular copies: 5 + 3 float4 per patch)
         for (int i = tid; i < TILE * 5; i += FF_THREADS) {
             int p = i / 5, q = i - p * 5;
@@ -274,6 +274,8 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
             s_rc[rl][cl] = f_rc;
             s_cr[cl][rl] = f_cr;
             unsigned m = __ballot_sync(0xffffffffu, trace);
+            unsigned mo = __ballot_sync(0xffffffffu, trace && r >= P.row0 && r < P.row1);
+            if (mo && lane == 0) atomicAdd(&s_nown, __popc(mo));
             if (m) {
                 int base = 0;
                 int leader = __ffs(m) - 1;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
         }
         __syncthreads();
         const int nlist = s_nlist;
-        if (tid == 0 && nlist) atomicAdd(P.pair_counter, (unsigned long long)nlist);
+        if (tid == 0 && nlist) { atomicAdd(P.pair_counter, (unsigned long long)nlist); atomicAdd(P.pair_counter + 1, (unsigned long long)s_nown); }
 
         // ---- phase 2: S visibility rays per listed pair; a warp claims 32 pairs at a time, lane = pair,
         // all lanes trace sample i together (neighbouring pairs + same sample => coherent rays)
@@ -373,10 +375,10 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     unsigned long long *d_pairs = nullptr;
     DZ_CUDA(cudaMalloc(&d_jobs, sizeof(int2) * (njobs ? njobs : 1)));
     DZ_CUDA(cudaMalloc(&d_counter, sizeof(int)));
-    DZ_CUDA(cudaMalloc(&d_pairs, sizeof(unsigned long long)));
+    DZ_CUDA(cudaMalloc(&d_pairs, 2 * sizeof(unsigned long long)));
     DZ_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(int2) * njobs, cudaMemcpyHostToDevice, st));
     DZ_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
-    DZ_CUDA(cudaMemsetAsync(d_pairs, 0, sizeof(unsigned long long), st));
+    DZ_CUDA(cudaMemsetAsync(d_pairs, 0, 2 * sizeof(unsigned long long), st));
     FFParams P;
     P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
     P.row0 = r0; P.row1 = r1;
@@ -400,12 +402,12 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     else k_ff_tiles<DAISY_FF_HOST><<<grid, FF_THREADS, smem, st>>>(P);
     DZ_CUDA(cudaGetLastError());
     DZ_CUDA(cudaEventRecord(e1, st));
-    unsigned long long pairs = 0;
-    DZ_CUDA(cudaMemcpyAsync(&pairs, d_pairs, sizeof(pairs), cudaMemcpyDeviceToHost, st));
+    unsigned long long pairs[2] = { 0, 0 };
+    DZ_CUDA(cudaMemcpyAsync(pairs, d_pairs, sizeof(pairs), cudaMemcpyDeviceToHost, st));
     DZ_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    if (write_F) { ctx->ff_ms = ms; ctx->pairs_traced = (int64_t)pairs; }
+    if (write_F) { ctx->ff_ms = ms; ctx->pairs_traced = (int64_t)pairs[0]; ctx->pairs_owned = (int64_t)pairs[1]; }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_jobs); cudaFree(d_counter); cudaFree(d_pairs);
     free(h_jobs);

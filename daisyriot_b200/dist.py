@@ -1,0 +1,130 @@
+"""Row-sharded form factors + gather across the GPUs of one box (one process per GPU, torch.distributed / NCCL).
+
+Each rank builds rows ``[rank*n, (rank+1)*n)`` of F against a replicated LBVH and owns that slice of B.  One gather
+pass is: local kernel -> in-place all-gather of this rank's residual block (``K x n`` floats + ``K`` partial band
+sums) over NVLink -> every rank totals the band sums in rank order, so all ranks take identical stop decisions
+with a single collective per pass (reference loop: ``visual studio/Lightning.h:145-151, 196-226``).
+
+The exchange itself is backend-agnostic (``exchange_pass``) so the host logic is testable on CPU with gloo."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def partition(N: int, rank: int, nranks: int):
+    """(row0, row1, rows_per_rank) -- must match ``set_partition`` in csrc/api.cu."""
+    n = (N + nranks - 1) // nranks
+    n = max(4, (n + 3) // 4 * 4)
+    return min(N, rank * n), min(N, (rank + 1) * n), n
+
+
+def block_layout(K_padded: int, n: int):
+    """(floats per exchange block, float offset of the K band-sum doubles) -- matches gather.cu."""
+    body = K_padded * n
+    return (body + 2 * K_padded + 3) // 4 * 4, body
+
+
+def padded_K(K: int) -> int:
+    return 1 if K <= 1 else 3 if K <= 3 else 9 if K <= 9 else 16 if K <= 16 else 32
+
+
+def exchange_pass(step_local, next_buffer, rank: int, nranks: int, group=None):
+    """One pass of the exchange protocol on any backend.
+
+    ``step_local()`` fills block ``rank`` of ``next_buffer`` (a 1-D tensor of ``nranks`` equal blocks); the in-place
+    all-gather then completes the buffer on every rank."""
+    import torch.distributed as dist
+    step_local()
+    if nranks > 1:
+        blk = next_buffer.numel() // nranks
+        dist.all_gather_into_tensor(next_buffer, next_buffer[rank * blk:(rank + 1) * blk], group=group)
+
+
+def total_band_sums(buffer_f32, K: int, K_padded: int, n: int, nranks: int) -> np.ndarray:
+    """Sum the per-rank partial band sums (doubles in each block's tail) in rank order."""
+    bstride, off = block_layout(K_padded, n)
+    host = buffer_f32.detach().cpu().numpy() if hasattr(buffer_f32, "detach") else np.asarray(buffer_f32)
+    out = np.zeros(K, np.float64)
+    for g in range(nranks):
+        tail = host[g * bstride + off: g * bstride + off + 2 * K_padded].view(np.float64)
+        out += tail[:K]
+    return out
+
+
+class _DevMem:
+    """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it without a copy."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class PartitionedSolver:
+    """A ``daisy_solver`` driven through the multi-GPU entry points with torch.distributed doing the exchange."""
+
+    def __init__(self, optixP, K, E, M, mat_idx, group=None):
+        import torch
+        self.torch = torch
+        self.p = optixP
+        self.K, self.rank, self.nranks, self.group = K, optixP.rank, optixP.nranks, group
+        L = _lib.lib()
+        self._s = C.c_void_p()
+        E = np.ascontiguousarray(E, np.float32)
+        M = np.ascontiguousarray(M, np.float32)
+        mat = np.ascontiguousarray(mat_idx, np.int32)
+        _lib.check(L.daisy_solver_create(optixP._ctx, K, _lib.fptr(E), _lib.fptr(M), M.shape[0], _lib.iptr(mat), C.byref(self._s)),
+                   "solver_create")
+        self._views = {}
+
+    def _next_view(self):
+        L = _lib.lib()
+        ptr, blk, tot = C.c_void_p(), C.c_int64(), C.c_int64()
+        _lib.check(L.daisy_solver_exchange_info(self._s, C.byref(ptr), C.byref(blk), C.byref(tot)))
+        if ptr.value not in self._views:
+            self._views[ptr.value] = self.torch.as_tensor(_DevMem(ptr.value, tot.value), device="cuda")
+        return self._views[ptr.value]
+
+    def step(self, want_sums: bool = False):
+        L = _lib.lib()
+        buf = self._next_view()
+        exchange_pass(lambda: _lib.check(L.daisy_solver_step_local(self._s), "step_local"), buf, self.rank, self.nranks, self.group)
+        if want_sums:
+            self.torch.cuda.current_stream().synchronize()
+            sums = np.zeros(self.K, np.float64)
+            _lib.check(L.daisy_solver_step_finish(self._s, sums.ctypes.data_as(C.POINTER(C.c_double))), "step_finish")
+            return sums
+        _lib.check(L.daisy_solver_step_finish(self._s, None), "step_finish")
+        return None
+
+    def band_sums(self):
+        sums = np.zeros(self.K, np.float64)
+        self.torch.cuda.current_stream().synchronize()
+        _lib.check(_lib.lib().daisy_solver_band_sums(self._s, sums.ctypes.data_as(C.POINTER(C.c_double))))
+        return sums
+
+    def reset(self):
+        _lib.check(_lib.lib().daisy_solver_reset(self._s))
+
+    def converge(self, threshold: float, per_band: bool, max_passes: int = 0) -> int:
+        passes = 0
+        sums = self.band_sums()
+        crit = (lambda s: (s > threshold).any()) if per_band else (lambda s: s.sum() > threshold)
+        while crit(sums) and (max_passes <= 0 or passes < max_passes):
+            sums = self.step(want_sums=True)
+            passes += 1
+        return passes
+
+    def read_local(self):
+        r0, r1 = self.p.row_range
+        B = np.empty((self.K, r1 - r0), np.float32)
+        R = np.empty((self.K, r1 - r0), np.float32)
+        _lib.check(_lib.lib().daisy_solver_read(self._s, _lib.fptr(B), _lib.fptr(R)))
+        return B, R
+
+    def close(self):
+        if self._s:
+            _lib.lib().daisy_solver_destroy(self._s)
+            self._s = None

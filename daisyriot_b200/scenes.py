@@ -229,3 +229,29 @@ def cornell_box(n_patches: int, n_fluorescent: int = 2, seed: int = 0x5EED) -> S
                np.asarray(M, np.int32), mats, f"cornell_{n_patches}")
     assert sc.numtriangles == n_patches, (sc.numtriangles, n_patches)
     return sc
+
+
+def write_obj(scene: Scene, directory: str, stem: str | None = None):
+    """Write ``scene`` as OBJ + MTL (the inverse of :func:`load_obj`; float32 values survive the round trip).
+    Lets the reference's own loader (``MeshS::loadFromFile``) read the synthetic scenes."""
+    stem = stem or (scene.name or "scene").replace(".obj", "")
+    obj, mtl = os.path.join(directory, stem + ".obj"), os.path.join(directory, stem + ".mtl")
+    with open(mtl, "w") as f:
+        for m in scene.materials:
+            f.write(f"newmtl {m['name']}\n")
+            for key in ("Kd", "Ks", "Ke"):
+                f.write(f"{key} {float(m[key][0]):.9g} {float(m[key][1]):.9g} {float(m[key][2]):.9g}\n")
+            f.write("\n")
+    with open(obj, "w") as f:
+        f.write(f"mtllib {stem}.mtl\no {stem}\n")
+        for v in scene.vertices:
+            f.write(f"v {float(v[0]):.9g} {float(v[1]):.9g} {float(v[2]):.9g}\n")
+        for v in scene.normals:
+            f.write(f"vn {float(v[0]):.9g} {float(v[1]):.9g} {float(v[2]):.9g}\n")
+        cur = None
+        for t, mi in zip(scene.tri, scene.mat_idx):
+            if mi != cur:
+                f.write(f"usemtl {scene.materials[mi]['name']}\n")
+                cur = mi
+            f.write(f"f {t[0]+1}//{t[3]+1} {t[1]+1}//{t[4]+1} {t[2]+1}//{t[5]+1}\n")
+    return obj, mtl

@@ -90,9 +90,12 @@ int daisy_formfactors_write_rows(daisy_ctx *ctx, int row0, int nrows, const floa
 /* parity aid: visibility hit masks of rows [row0,row0+nrows): out[(r-row0)*N + c], bit i = sample i of the pair
  * (min(r,c) -> max(r,c)) saw its destination (the test at VS/OptixPrimeFunctionality.cpp:208); 0 if not traced. */
 int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int nrows, uint64_t *out);
-/* what the last daisy_formfactors_build did: pairs traced (unique, this context), rays, and device milliseconds
- * of the LBVH build and of the fused form-factor/visibility kernel */
-int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *rays, double *lbvh_ms, double *ff_ms);
+/* what the last daisy_formfactors_build did: mutually facing pairs this context traced, how many of those have
+ * their lower patch index inside this context's row range (summing that over all ranks counts every pair of the
+ * matrix once), rays cast (= pairs_traced * S), and device milliseconds of the LBVH build and of the fused
+ * form-factor/visibility kernel */
+int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *pairs_owned, int64_t *rays, double *lbvh_ms,
+                            double *ff_ms);
 
 /* ---- radiosity / fluorescence gather ------------------------------------------------------------------------
  * replaces the Lightning family (VS/Lightning.h): residual <- M (F residual); B += residual

@@ -75,6 +75,23 @@ def _fp(a):
     return a.ctypes.data_as(C.POINTER(C.c_float))
 
 
+class _quiet_stdout:
+    """The reference's C code printf()s while loading tables; keep that off the caller's stdout (fd 1)."""
+
+    def __enter__(self):
+        import sys
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        lib().ref_flush_stdout()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        os.close(self.null)
+
+
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
@@ -95,6 +112,7 @@ class RefScene:
         old = os.getcwd()
         os.chdir(coeff_cwd)
         try:
+          with _quiet_stdout():
             h = lib().ref_scene_load(os.path.abspath(obj).encode() if os.path.isabs(obj) else obj.encode(),
                                      mtl_dir.encode(), _fp(wl), wl.size)
         finally:

@@ -57,6 +57,8 @@ static void quiet(bool on) {
 
 extern "C" {
 
+void ref_flush_stdout(void) { fflush(stdout); }
+
 // ---- scene -------------------------------------------------------------------------------------
 // MeshS::loadFromFile (MeshS.cpp:22-128).  cwd must hold color_tables/srgb.coeff (Material.cpp:11).
 void *ref_scene_load(const char *obj, const char *mtl_dir, const float *wavelengths, int nw) {

@@ -109,7 +109,7 @@ def test_radmat_small_bitexact_vs_bruteforce(dz, cornell512, uv50, variant):
         assert np.array_equal(masks[traced], m_ref[traced])
     assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
     st = p.stats()
-    assert st["rays"] == st["pairs_traced"] * 50 and st["pairs_traced"] > 0
+    assert st["rays"] == st["pairs_traced"] * 50 and st["pairs_traced"] > 0 and st["pairs_owned"] == st["pairs_traced"]
     # masks are symmetric, the matrix has an empty diagonal, a closed-ish box keeps row sums bounded
     assert np.array_equal(masks, masks.T) and not F.diagonal().any()
     # CSC hand-back equals the dense matrix
