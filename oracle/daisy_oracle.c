@@ -471,3 +471,41 @@ int orc_num_procs(void) {
     return 1;
 #endif
 }
+
+/* Upper-triangle form of orc_radmat_rows (direct variant only): for r in [row0,row1) and c > r writes
+ * F_rc[(r-row0)*N+c] = RadMat(r,c), F_cr[(r-row0)*N+c] = RadMat(c,r) and the pair's mask; entries with c <= r are 0.
+ * Used to generate whole-matrix golden checksums without tracing every pair twice. */
+int64_t orc_radmat_upper(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, int row0, int row1,
+                         int variant, float *F_rc, float *F_cr, uint64_t *masks_out, int nthreads) {
+    int N = m->ntri;
+    int64_t rays = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : rays)
+    for (int r = row0; r < row1; r++) {
+        for (int c = 0; c < N; c++) {
+            int64_t o = (int64_t)(r - row0) * N + c;
+            float v_rc = 0.0f, v_cr = 0.0f; uint64_t mask = 0;
+            if (c > r) {
+                float ff_rc = orc_p2p_ff(m, r, c, variant);
+                if (ff_rc > 0.0f) {
+                    mask = pair_mask(m, b, uv, S, r, c, 0); rays += S;
+                    float visibility = 0;
+                    for (int i = 0; i < S; i++) visibility += ((mask >> i) & 1) ? 1.0f : 0.0f;
+                    visibility = visibility / S;
+                    if (visibility > 0) {
+                        float ff_cr = orc_p2p_ff(m, c, r, variant);
+                        ff_cr = (ff_cr > 0.0) ? ff_cr : 0.0f;
+                        v_rc = (float)((double)visibility * (double)ff_rc);
+                        v_cr = (float)((double)visibility * (double)ff_cr);
+                    }
+                }
+            }
+            if (F_rc) F_rc[o] = v_rc;
+            if (F_cr) F_cr[o] = v_cr;
+            if (masks_out) masks_out[o] = mask;
+        }
+    }
+    return rays;
+}

@@ -74,6 +74,10 @@ int64_t orc_radmat_rows(const orc_mesh *m, const orc_bvh *b, const float *uv, in
                         int variant, int reciprocity, int brute, float *F_out, uint64_t *masks_out,
                         int nthreads);
 
+/* upper-triangle form (c > r only): F_rc = RadMat(r,c), F_cr = RadMat(c,r), masks; direct variant */
+int64_t orc_radmat_upper(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, int row0, int row1,
+                         int variant, float *F_rc, float *F_cr, uint64_t *masks_out, int nthreads);
+
 /* gather ----------------------------------------------------------------------------------- */
 /* one pass of VS/Lightning.h:196-226 on a dense row-major F (N x ldF):
  *   bounced_k = F * res_k ; res'[:,p] = M[mat[p]] * bounced[:,p] ; B_k += res'_k

@@ -56,6 +56,9 @@ def lib():
         L.orc_radmat_rows.restype = C.c_int64
         L.orc_radmat_rows.argtypes = [C.POINTER(_Mesh), C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, fp, C.POINTER(C.c_uint64), C.c_int]
+        L.orc_radmat_upper.restype = C.c_int64
+        L.orc_radmat_upper.argtypes = [C.POINTER(_Mesh), C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp,
+                                       C.POINTER(C.c_uint64), C.c_int]
         L.orc_gather_pass.argtypes = [fp, C.c_int64, C.c_int, C.c_int, fp, fp, fp, ip, C.c_int,
                                       C.POINTER(C.c_double), C.c_int]
         L.orc_num_procs.restype = C.c_int
@@ -135,6 +138,25 @@ class Oracle:
                                       int(reciprocity), int(brute), _fp(F),
                                       masks.ctypes.data_as(C.POINTER(C.c_uint64)) if want_masks else None, nthreads)
         return F, masks, int(rays)
+
+    def radmat_upper(self, uv, row0, row1, variant=0, nthreads=0):
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        F_rc = np.empty((row1 - row0, self.N), np.float32)
+        F_cr = np.empty((row1 - row0, self.N), np.float32)
+        masks = np.empty((row1 - row0, self.N), np.uint64)
+        rays = self.L.orc_radmat_upper(C.byref(self.mesh), self.bvh, _fp(uv), uv.shape[0], row0, row1, variant, _fp(F_rc), _fp(F_cr),
+                                       masks.ctypes.data_as(C.POINTER(C.c_uint64)), nthreads)
+        return F_rc, F_cr, masks, int(rays)
+
+
+def row_checksums(F_rows, mask_rows):
+    """Order-free per-row digests used by the whole-matrix golden files:
+    (sum over columns of mask*(2c+1) mod 2^64, float64 row sum of F, xor of the F bit patterns)."""
+    N = F_rows.shape[1]
+    w = (2 * np.arange(N, dtype=np.uint64) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        mh = (mask_rows * w[None, :]).sum(axis=1, dtype=np.uint64)
+    return mh, F_rows.astype(np.float64).sum(axis=1), np.bitwise_xor.reduce(F_rows.view(np.uint32), axis=1)
 
 
 def ray_tri(ray6, a, b, c):

@@ -1,0 +1,151 @@
+"""CPU suite: the C-ABI library loads and exports exactly what include/daisy_b200.h declares (no compute calls
+without a GPU), plus the host-side logic around it."""
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from daisyriot_b200 import _lib, api, dist, materials, rgb2spec, scenes
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "daisy_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return set(re.findall(r"\b(daisy_[a-z0-9_]+)\s*\(", txt))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    assert os.path.exists(_lib.SO_PATH), "build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()')"
+    L = ctypes.CDLL(_lib.SO_PATH)
+    declared = _header_symbols()
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().daisy_version() >= 100
+
+
+def test_library_is_sm100a_cuda_with_tma():
+    # the product is the CUDA library: its SASS must be sm_100a and contain the TMA bulk copy of the gather kernel
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-sass", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out and "k_gather_partial" in out and "k_ff_tiles" in out
+
+
+def test_errors_without_a_gpu_are_reported_not_faked():
+    import ctypes as C
+    L = _lib.lib()
+    if L.daisy_device_count() > 0:
+        pytest.skip("a GPU is present")
+    ctx = C.c_void_p()
+    v = np.zeros((3, 3), np.float32); n = np.zeros((1, 3), np.float32); t = np.array([[0, 1, 2, 0, 0, 0]], np.int32)
+    rc = L.daisy_ctx_create(_lib.fptr(v), 3, _lib.fptr(n), 1, _lib.iptr(t), 1, 0, C.byref(ctx))
+    assert rc != 0 and not ctx.value and L.daisy_last_error()
+    with pytest.raises(_lib.DaisyError):
+        api.OptixPrimeFunctionality(api.MeshS.from_scene(scenes.cornell_box(32)))  # no silent CPU fallback
+    bad = np.array([[0, 1, 7, 0, 0, 0]], np.int32)
+    assert L.daisy_ctx_create(_lib.fptr(v), 3, _lib.fptr(n), 1, _lib.iptr(bad), 1, 0, C.byref(ctx)) == -1
+
+
+def test_msvc_sample_pattern():
+    uv = scenes.msvc_sample_pattern(1)
+    assert uv.shape == (50, 2) and uv.dtype == np.float32
+    # MSVC rand() with srand(1) starts 41, 18467, 6334, ...
+    assert uv[0, 0] == np.float32(41) / np.float32(32767)
+    assert uv[0, 1] == np.float32(np.float32(18467) / np.float32(32767)) * np.float32(np.float32(1) - uv[0, 0])
+    assert (uv >= 0).all() and (uv.sum(1) < 1).all()
+    assert not np.array_equal(uv, scenes.msvc_sample_pattern(2))
+
+
+def test_cornell_generator_and_obj_roundtrip(tmp_path):
+    for n in (32, 512, 2048):
+        sc = scenes.cornell_box(n)
+        assert sc.numtriangles == n and sc.tri.max() < len(sc.vertices) and sc.tri[:, 3:].max() < len(sc.normals)
+        a, b, c = (sc.vertices[sc.tri[:, k]] for k in range(3))
+        geo = np.cross(b - a, c - a)
+        nrm = sc.normals[sc.tri[:, 3]]
+        assert ((geo * nrm).sum(1) > 0).all()  # winding agrees with the stored normals
+        assert (np.linalg.norm(geo, axis=1) > 0).all()
+    with pytest.raises(ValueError):
+        scenes.cornell_box(1000)
+    sc = scenes.cornell_box(512, n_fluorescent=5)
+    obj, _ = scenes.write_obj(sc, str(tmp_path))
+    s2 = scenes.load_obj(obj, str(tmp_path))
+    assert np.array_equal(sc.vertices, s2.vertices) and np.array_equal(sc.tri, s2.tri) and np.array_equal(sc.mat_idx, s2.mat_idx)
+    scenes.save_scene_npz(sc, str(tmp_path / "s.npz"))
+    s3 = scenes.load_scene_npz(str(tmp_path / "s.npz"))
+    assert np.array_equal(sc.tri, s3.tri) and [m["name"] for m in s3.materials] == [m["name"] for m in sc.materials]
+
+
+def test_fixture_scenes_have_the_surveyed_shape(fixture_scenes):
+    cb, balls = fixture_scenes["cornellbox_blacklight"], fixture_scenes["colorballs"]
+    assert (cb.numtriangles, len(cb.vertices), len(cb.normals)) == (7712, 4360, 304)
+    assert (balls.numtriangles, len(balls.vertices), len(balls.normals)) == (6400, 3373, 2551)
+    assert list(np.bincount(cb.mat_idx)) == [32, 2560, 2560, 2560]
+
+
+def test_material_classification_and_matrices(coeff_model, fixture_scenes):
+    model, _ = coeff_model
+    wl = np.arange(200, 601, 50).astype(np.float32)
+    mats = materials.make_materials(fixture_scenes["cornellbox_blacklight"].materials, wl, model)
+    assert [m.kind for m in mats] == ["uvlight", "fluorescent", "fluorescent", "diffuse"]
+    lamp, pink, _, white = mats
+    assert not lamp.M.any() and lamp.spectral_emission[3] == 1.0 and lamp.spectral_emission[0] < 1e-30  # bell curve at 350 nm
+    assert np.array_equal(np.diag(white.M), white.spectral_values) and not (white.M - np.diag(np.diag(white.M))).any()
+    uvcol = 3  # 350 nm is the only band inside (300, 400)
+    off = pink.M.copy(); off[:, uvcol] = 0
+    assert np.array_equal(off, np.eye(9, dtype=np.float32) * (np.arange(9) != uvcol))
+    assert np.isnan(white.spectral_emission).all()  # Ke = 0 -> 0*inf in rgb2spec_fetch; filtered by `> 0` downstream
+    E, M = materials.spectral_inputs(mats, fixture_scenes["cornellbox_blacklight"].mat_idx, 7.0)
+    assert E.shape == (9, 7712) and np.isfinite(E).all() and E[3, 0] == 0 and E[3].max() == 7.0
+    assert M.shape == (4, 9, 9) and M[1, uvcol, 0] == pink.M[0, uvcol]  # column-major per material
+    balls = materials.make_materials(fixture_scenes["colorballs"].materials, wl, model)
+    assert [m.kind for m in balls] == ["diffuse"] * 4 + ["fluorescent"]  # "white" has Ks = 0.5 => fluorescent
+    Ergb, Mrgb = materials.rgb_inputs(balls, fixture_scenes["colorballs"].mat_idx, 2.0)
+    assert Ergb.shape == (3, 6400) and Ergb.max() == np.float32(1.6) * np.float32(2.0) and Mrgb[1, 0, 0] == np.float32(0.8)
+
+
+def test_rgb2spec_table_roundtrip(tmp_path):
+    p = str(tmp_path / "t.coeff")
+    rgb2spec.write_surrogate_table(p, 8)
+    m = rgb2spec.RGB2Spec.load(p)
+    assert m.res == 8 and m.scale[0] == 0 and m.scale[-1] == 1 and m.data.size == 3 * 8 ** 3 * 3
+    s = [rgb2spec.eval_precise(m.fetch([0.2, 0.5, 0.9]), w) for w in (400, 500, 600)]
+    assert all(0 < v < 1 for v in s)
+    with open(p, "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(ValueError):
+        rgb2spec.RGB2Spec.load(p)
+
+
+def test_matrix_cache_file_format(tmp_path):
+    # Lightning::SerializeMat layout (Lightning.h:21-50): 5 ints, values, outerIndex[outerSize], innerIndex
+    rng = np.random.RandomState(0)
+    D = (rng.uniform(0, 1, (7, 7)) * (rng.uniform(0, 1, (7, 7)) < 0.4)).astype(np.float32)
+    vals, inner, outer = [], [], [0]
+    for c in range(7):
+        nz = np.nonzero(D[:, c])[0]
+        vals += list(D[nz, c]); inner += list(nz); outer.append(len(vals))
+    p = str(tmp_path / "m")
+    api.serialize_mat(p, np.array(vals, np.float32), np.array(inner, np.int32), np.array(outer, np.int32), 7)
+    raw = open(p, "rb").read()
+    assert struct.unpack("<5i", raw[:20]) == (7, 7, len(vals), 7, 7) and len(raw) == 20 + 4 * len(vals) * 2 + 4 * 7
+    assert np.array_equal(api.deserialize_mat(p), D)
+
+
+def test_partition_and_exchange_layout():
+    assert dist.partition(131072, 3, 8) == (49152, 65536, 16384)
+    assert dist.partition(7712, 7, 8) == (6748, 7712, 964)
+    assert dist.partition(6401, 0, 2) == (0, 3204, 3204)     # 3201 rounded up to a multiple of 4
+    assert dist.partition(10, 3, 4) == (10, 10, 4)          # more blocks than rows: empty tail rank
+    assert dist.block_layout(9, 964) == (8696, 8676)         # K*n floats + K doubles, padded to 16 B
+    assert [dist.padded_K(k) for k in (1, 2, 3, 9, 12, 17, 32)] == [1, 3, 3, 9, 16, 32, 32]
+    x = api.cie1931WavelengthToXYZFit(550.0)
+    assert x.dtype == np.float32 and abs(x[1] - 0.99) < 0.02
