@@ -1,0 +1,30 @@
+// demo_main.cpp -- the reference's start-up sequence (main.cpp:94-108) without the window: load the scene with the
+// reference's own MeshS/Material code, build form factors and converge the lighting through the shim classes.
+//   shim_demo <scene.obj> <mtl_dir/> <method 0|1|2> <emission_value> <seed>      (cwd must hold color_tables/srgb.coeff)
+// Prints one line of results the parity test compares with the Python path.
+#include <cstdio>
+#include <vector>
+#define TINYOBJLOADER_IMPLEMENTATION
+#include <tiny_obj_loader.h>
+#undef TINYOBJLOADER_IMPLEMENTATION
+#include "OptixPrimeFunctionality.h"
+#include "Lightning.h"
+
+int main(int argc, char **argv) {
+    if (argc < 6) { fprintf(stderr, "usage: shim_demo scene.obj mtl_dir/ method emission seed\n"); return 2; }
+    std::vector<float> wavelengths = { 200.0, 250.0, 300.0, 350.0, 400.0, 450.0, 500.0, 550.0, 600.0 }; // main.cpp:94
+    MeshS mesh(argv[1], argv[2], wavelengths);
+    for (auto &m : mesh.materials) // the UV lamp's M is undefined behaviour in the reference (Material.cpp:52-54): use M = 0
+        if (m.spectral_values.size() && m.spectral_values[0] == 0.0f && m.spectral_values.back() == 0.0f && m.rgbcolor == glm::vec3(0.f))
+            m.M.setZero();
+    OptixPrimeFunctionality optixP(mesh, 0, atol(argv[5]));
+    float emission = (float)atof(argv[4]);
+    int method = atoi(argv[3]);
+    Lightning *l = Lightning::get_lightning(method, mesh, optixP, emission, wavelengths, true, nullptr);
+    double sum = 0;
+    for (auto &band : l->lightningvalues) for (float v : band) sum += v;
+    glm::vec3 c = l->get_color_of_patch(mesh.numtriangles / 2);
+    printf("RESULT passes=%d sumB=%.9e color=%.6f,%.6f,%.6f rand0=%.9g\n", l->numpasses, sum, c.x, c.y, c.z, optixP.rands[0].u);
+    delete l;
+    return 0;
+}

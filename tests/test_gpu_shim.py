@@ -1,0 +1,42 @@
+"""The C++ drop-in classes (shim/OptixPrimeFunctionality.h, shim/Lightning.h) driven the way the reference's main()
+drives them, against the Python mirror on the same scene and sample pattern."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+DEMO = os.path.join(ROOT, "shim", "_build", "shim_demo")
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO), reason="shim demo is built where /root/reference exists (make -C shim)")
+@pytest.mark.parametrize("method", [2, 1])
+def test_cpp_shim_matches_python_mirror(tmp_path, coeff_model, uv50, method):
+    import daisyriot_b200 as dz
+    from daisyriot_b200 import scenes
+    model, cwd = coeff_model
+    sc = scenes.cornell_box(2048)
+    if method == 1:  # give the RGB flavour something to emit (the UV lamp has no RGB emission)
+        sc.materials[3]["Ke"] = np.array([0.2, 0.1, 0.05], np.float32)
+    obj, _ = scenes.write_obj(sc, cwd, "shim_scene%d" % method)
+    rands = os.path.join(cwd, "rands.bin")
+    uv50.astype(np.float32).tofile(rands)
+    ev = 7.0 if method == 2 else 500.0
+    out = subprocess.run([DEMO, obj, cwd + "/", str(method), str(ev), "1", rands], cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    m = re.search(r"RESULT passes=(\d+) sumB=(\S+) color=(\S+),(\S+),(\S+)", out.stdout)
+    assert m, out.stdout[-2000:]
+    wl = np.arange(200, 601, 50).astype(np.float32)
+    mesh = dz.MeshS.from_scene(sc, wl, model)
+    p = dz.OptixPrimeFunctionality(mesh, rands=uv50)
+    lt = dz.Lightning.get_lightning(method, mesh, p, ev, wl, True, None)
+    B = lt.lightningvalues
+    assert int(m.group(1)) == lt.numpasses and lt.numpasses > 0
+    assert abs(float(m.group(2)) - B.astype(np.float64).sum()) <= 1e-6 * abs(B.astype(np.float64).sum())
+    c = lt.get_color_of_patch(sc.numtriangles // 2)
+    assert np.allclose([float(m.group(i)) for i in (3, 4, 5)], c, rtol=1e-4, atol=1e-5)
+    lt.close(); p.close()
