@@ -1,6 +1,6 @@
 // demo_main.cpp -- the reference's start-up sequence (main.cpp:94-108) without the window: load the scene with the
 // reference's own MeshS/Material code, build form factors and converge the lighting through the shim classes.
-//   shim_demo <scene.obj> <mtl_dir/> <method 0|1|2> <emission_value> <seed>      (cwd must hold color_tables/srgb.coeff)
+//   shim_demo <scene.obj> <mtl_dir/> <method 0|1|2> <emission_value> <seed> [rands.bin]   (cwd must hold color_tables/srgb.coeff)
 // Prints one line of results the parity test compares with the Python path.
 #include <cstdio>
 #include <vector>
@@ -18,6 +18,12 @@ int main(int argc, char **argv) {
         if (m.spectral_values.size() && m.spectral_values[0] == 0.0f && m.spectral_values.back() == 0.0f && m.rgbcolor == glm::vec3(0.f))
             m.M.setZero();
     OptixPrimeFunctionality optixP(mesh, 0, atol(argv[5]));
+    if (argc > 6) { // optional: a binary file of S x {u,v} floats replaces the rand() pattern (repeatable across C runtimes)
+        std::vector<UV> r(RAYS_PER_PATCH);
+        FILE *f = fopen(argv[6], "rb");
+        if (f && fread(r.data(), sizeof(UV), r.size(), f) == r.size()) optixP.setSamples(r);
+        if (f) fclose(f);
+    }
     float emission = (float)atof(argv[4]);
     int method = atoi(argv[3]);
     Lightning *l = Lightning::get_lightning(method, mesh, optixP, emission, wavelengths, true, nullptr);
