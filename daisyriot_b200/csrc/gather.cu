@@ -13,6 +13,7 @@
 // registers.  k_gather_epilogue sums the column-range partials, applies the per-material KxK matrix, accumulates
 // B, writes the new residual into the exchange block of this rank and totals the per-band residual sums.
 #include "daisy_common.cuh"
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,6 +40,9 @@ struct daisy_solver {
     double *d_cta_sums = nullptr;
     unsigned int *d_done = nullptr;
     int R = 8, nsplit = 1, grid = 148, colw = 0;
+    bool use_tma = true;
+    alignas(64) CUtensorMap tmF;        // F rows of this rank: 2-D (ldF x nloc), box 128 x tile rows
+    alignas(64) CUtensorMap tmRes[2];   // exchange buffers: 3-D (n x Kp x G), box 128 x Kp x 1
     int numpasses = 0;
     double last_ms = 0.0;
     std::vector<double> sums;   // band sums of the current residual
@@ -66,6 +70,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// tiled TMA loads through a tensor map (SASS: UTMALDG); out-of-range parts of the box are zero-filled
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float4 ldg_stream(const float *p) {
     float4 r;
@@ -198,6 +211,134 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gather_partial(GatherParams P)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// k_gather_tma: the same work decomposition with a register-free load pipeline.  Warp 8 is the producer: for every
+// 128-column step it fills one shared-memory stage -- the 64x128 F tile as 64 row segments plus the K residual band
+// slices -- with 1-D TMA bulk copies that complete on the stage's "full" mbarrier.  Warps 0-7 consume: LDS.128 of their
+// 8 F rows and the K band slices, K FMAs per F element, then one arrive on the stage's "empty" mbarrier.  Up to
+// NSTAGE x (64+K) x 512 B (~219 KB for K=9) are in flight per SM without holding a single register, and there is no
+// CTA-wide barrier in the loop.
+#define T_COLS 128
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// rows per consumer warp / consumer warps per CTA: the K accumulators of RW rows must fit the register file
+template <int K> struct TmaCfg { static constexpr int RW = 8, NCW = 8; };   // K <= 9 : 64-row tiles, 9 warps
+template <> struct TmaCfg<16> { static constexpr int RW = 4, NCW = 16; };   // 64-row tiles, 17 warps
+template <> struct TmaCfg<32> { static constexpr int RW = 4, NCW = 8; };    // 32-row tiles, 9 warps (FP32-pipe bound anyway)
+template <int K>
+__host__ __device__ constexpr int tma_rows() { return TmaCfg<K>::RW * TmaCfg<K>::NCW; }
+template <int K>
+__host__ __device__ constexpr int tma_stage_bytes() { return (tma_rows<K>() + K) * T_COLS * 4; }
+template <int K>
+__host__ __device__ constexpr int tma_nstage() { return (227 * 1024 - 256) / tma_stage_bytes<K>() > 8 ? 8 : (227 * 1024 - 256) / tma_stage_bytes<K>(); }
+
+template <int K>
+__global__ void __launch_bounds__((TmaCfg<K>::NCW + 1) * 32, 1)
+k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmRes) {
+    constexpr int NST = tma_nstage<K>();
+    constexpr int STAGE_F = tma_stage_bytes<K>() / 4; // floats per stage
+    constexpr int RW = TmaCfg<K>::RW, NCW = TmaCfg<K>::NCW, T_ROWS = RW * NCW;
+    extern __shared__ __align__(128) unsigned char g_smem[];
+    float *stages = reinterpret_cast<float *>(g_smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(g_smem + (size_t)NST * tma_stage_bytes<K>());
+    uint64_t *empty = full + NST;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NST; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nitems = P.nrb * P.nsplit;
+    uint32_t it = 0; // global step counter: stage = it % NST, phase = (it / NST) & 1
+    if (warp == NCW) {
+        // ------------------------------- producer -------------------------------
+        // one elected lane issues two tiled TMA loads per stage: the T_ROWS x 128 block of F and the K x 128 block
+        // of the residual bands (tiles never straddle an exchange block: n is a multiple of 128 when G > 1, and a
+        // single block's tail beyond n is zero-filled by the TMA unit)
+        if (lane == 0) {
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int rb = item / P.nsplit, split = item - rb * P.nsplit;
+                const int c_begin = split * P.colw;
+                const int c_end = min(P.ncols, c_begin + P.colw);
+                const int nstep = (c_end - c_begin + T_COLS - 1) / T_COLS;
+                const int row0 = rb * T_ROWS;
+                for (int s = 0; s < nstep; s++, it++) {
+                    const int st = it % NST;
+                    mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
+                    const int col0 = c_begin + s * T_COLS;
+                    float *sf = stages + (size_t)st * STAGE_F;
+                    mbar_expect_tx(&full[st], (uint32_t)tma_stage_bytes<K>());
+                    tma_load_2d(sf, &tmF, col0, row0, &full[st]);
+                    const int g = col0 / P.n, jl = col0 - g * P.n;
+                    tma_load_3d(sf + T_ROWS * T_COLS, &tmRes, jl, 0, g, &full[st]);
+                }
+            }
+        }
+    } else {
+        // ------------------------------- consumers ------------------------------
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int rb = item / P.nsplit, split = item - rb * P.nsplit;
+            const int c_begin = split * P.colw;
+            const int c_end = min(P.ncols, c_begin + P.colw);
+            const int nstep = (c_end - c_begin + T_COLS - 1) / T_COLS;
+            const int row_base = rb * T_ROWS + warp * RW;
+            float acc[RW][K];
+#pragma unroll
+            for (int r = 0; r < RW; r++)
+#pragma unroll
+                for (int k = 0; k < K; k++) acc[r][k] = 0.0f;
+            for (int s = 0; s < nstep; s++, it++) {
+                const int st = it % NST;
+                mbar_wait(&full[st], (it / NST) & 1);
+                const float *sf = stages + (size_t)st * STAGE_F + lane * 4;
+                {
+                    float4 f[RW];
+#pragma unroll
+                    for (int r = 0; r < RW; r++) f[r] = *reinterpret_cast<const float4 *>(sf + (warp * RW + r) * T_COLS);
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        float4 x = *reinterpret_cast<const float4 *>(sf + (T_ROWS + k) * T_COLS);
+#pragma unroll
+                        for (int r = 0; r < RW; r++) {
+                            acc[r][k] = fmaf(f[r].x, x.x, acc[r][k]);
+                            acc[r][k] = fmaf(f[r].y, x.y, acc[r][k]);
+                            acc[r][k] = fmaf(f[r].z, x.z, acc[r][k]);
+                            acc[r][k] = fmaf(f[r].w, x.w, acc[r][k]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+            }
+#pragma unroll
+            for (int r = 0; r < RW; r++)
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    float v = acc[r][k];
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    acc[r][k] = v;
+                }
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < RW; r++) {
+                    int row = row_base + r;
+                    if (row < P.nloc) {
+                        float *dst = P.partial + ((size_t)split * P.nloc + row) * K;
+#pragma unroll
+                        for (int k = 0; k < K; k++) dst[k] = acc[r][k];
+                    }
+                }
+            }
+        }
+    }
+}
+
 struct EpiParams {
     const float *partial; int nsplit, nloc, n;
     const float *M; const int *mat;
@@ -288,7 +429,19 @@ static int launch_pass_K(daisy_solver *s) {
     P.res = s->d_res[s->cur]; P.bstride = s->bstride; P.partial = s->d_partial;
     P.nsplit = s->nsplit; P.colw = s->colw; P.nrb = (s->nloc + G_WARPS * s->R - 1) / (G_WARPS * s->R);
     int rc;
-    if constexpr (K <= 9) {
+    if (s->use_tma) {
+        constexpr int NST = tma_nstage<K>();
+        size_t smem = (size_t)NST * tma_stage_bytes<K>() + 2 * NST * sizeof(uint64_t);
+        static bool attr_done = false;
+        if (!attr_done) {
+            DZ_CUDA(cudaFuncSetAttribute(k_gather_tma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        P.nrb = (s->nloc + tma_rows<K>() - 1) / tma_rows<K>();
+        k_gather_tma<K><<<s->grid, (TmaCfg<K>::NCW + 1) * 32, smem, c->stream>>>(P, s->tmF, s->tmRes[s->cur]);
+        DZ_CUDA(cudaGetLastError());
+        rc = DAISY_OK;
+    } else if constexpr (K <= 9) {
         rc = (s->R == 8) ? launch_partial<K, 8>(s, P) : launch_partial<K, 4>(s, P);
     } else {
         rc = (s->R == 4) ? launch_partial<K, 4>(s, P) : launch_partial<K, 2>(s, P);
@@ -319,12 +472,56 @@ static int launch_pass(daisy_solver *s) {
     return DAISY_E_INVALID;
 }
 
+// ---- tensor maps (driver entry point fetched through the runtime; no libcuda link dependency) ------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_maps(daisy_solver *s) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { daisy_set_error("cuTensorMapEncodeTiled is not available from this driver"); return DAISY_E_CUDA; }
+    daisy_ctx *c = s->ctx;
+    int trows = (s->Kp == 32) ? 32 : 64;
+    {
+        cuuint64_t dims[2] = { (cuuint64_t)c->ldF, (cuuint64_t)(s->nloc > 0 ? s->nloc : 1) };
+        cuuint64_t strides[1] = { (cuuint64_t)c->ldF * 4 };
+        cuuint32_t box[2] = { 128, (cuuint32_t)trows };
+        cuuint32_t es[2] = { 1, 1 };
+        CUresult r = enc(&s->tmF, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->d_F, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { daisy_set_error("cuTensorMapEncodeTiled(F) failed: %d", (int)r); return DAISY_E_CUDA; }
+    }
+    for (int b = 0; b < 2; b++) {
+        cuuint64_t dims[3] = { (cuuint64_t)s->n, (cuuint64_t)s->Kp, (cuuint64_t)s->G };
+        cuuint64_t strides[2] = { (cuuint64_t)s->n * 4, (cuuint64_t)s->bstride * 4 };
+        cuuint32_t box[3] = { 128, (cuuint32_t)s->Kp, 1 };
+        cuuint32_t es[3] = { 1, 1, 1 };
+        CUresult r = enc(&s->tmRes[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->d_res[b], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { daisy_set_error("cuTensorMapEncodeTiled(residual) failed: %d", (int)r); return DAISY_E_CUDA; }
+    }
+    return DAISY_OK;
+}
+
 // choose rows-per-warp and the column split so that (row blocks x splits) fills the persistent grid evenly
 static void plan(daisy_solver *s) {
     int sms = s->ctx->num_sms;
     s->grid = sms;
+    const char *env = getenv("DAISY_GATHER");
+    s->use_tma = !(env && strcmp(env, "ldg") == 0);
     int Rs[2];
-    if (s->Kp <= 9) { Rs[0] = 8; Rs[1] = 4; } else { Rs[0] = 2; Rs[1] = 4; }
+    if (s->use_tma) { Rs[0] = Rs[1] = (s->Kp == 32 ? 4 : 8); } // rows per block / G_WARPS: 64-row tiles, 32-row for K=32
+    else if (s->Kp <= 9) { Rs[0] = 8; Rs[1] = 4; } else { Rs[0] = 2; Rs[1] = 4; }
     int ncols = s->G * s->n;
     int maxsplit = (ncols + 4 * G_TC - 1) / (4 * G_TC); // keep at least 2048 columns per item
     if (maxsplit < 1) maxsplit = 1;
@@ -342,7 +539,7 @@ static void plan(daisy_solver *s) {
         }
     }
     int colw = (ncols + s->nsplit - 1) / s->nsplit;
-    s->colw = ((colw + G_TC - 1) / G_TC) * G_TC;
+    s->colw = ((colw + G_TC - 1) / G_TC) * G_TC; // multiple of 512 columns (and of the 128-column TMA step)
     s->nsplit = (ncols + s->colw - 1) / s->colw;
 }
 
@@ -414,6 +611,7 @@ extern "C" int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const 
     SC(cudaMemset(s->d_res[1], 0, exb));
     SC(cudaEventCreate(&s->e0));
     SC(cudaEventCreate(&s->e1));
+    if (s->use_tma) { int mrc = make_maps(s); if (mrc) { free_solver(s); return mrc; } }
     {
         std::vector<float> ex;
         to_exchange(s, E, ex);

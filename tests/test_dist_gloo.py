@@ -105,5 +105,5 @@ def test_two_rank_exchange_matches_single_process(tmp_path):
     assert np.allclose(outs[0]["sums"], outs[1]["sums"], rtol=0, atol=0)       # identical stop inputs on all ranks
     assert np.allclose(outs[0]["sums"], sums, rtol=1e-6)
     Bcat = np.concatenate([o["B"] for o in outs], axis=1)
-    assert [int(o["r0"]) for o in outs] == [0, 256] and int(outs[1]["r1"]) == N_use
+    assert [int(o["r0"]) for o in outs] == [0, 256] and int(outs[1]["r1"]) == N_use  # 255 -> 256 rows per block
     assert np.allclose(Bcat, B, rtol=2e-6, atol=1e-7 * np.abs(B).max())
