@@ -26,7 +26,7 @@ extern "C" int daisy_device_count(void) {
 
 static void free_ctx(daisy_ctx *c) {
     if (!c) return;
-    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_geom);
+    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom);
     cudaFree(c->d_nodes); cudaFree(c->d_F);
     delete c;
 }
@@ -301,6 +301,8 @@ extern "C" int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int
     if (e != cudaSuccess) { daisy_set_error("daisy_visibility_masks: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
     return rc;
 }
+
+extern "C" int64_t daisy_formfactors_pairs_fallback(daisy_ctx *ctx) { return ctx ? ctx->pairs_heavy : -1; }
 
 extern "C" int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *pairs_owned, int64_t *rays, double *lbvh_ms, double *ff_ms) {
     DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_formfactors_stats: null context");

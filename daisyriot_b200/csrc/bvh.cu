@@ -128,7 +128,7 @@ __global__ void k_hierarchy(const uint64_t *__restrict__ keys, int N, int2 *__re
 // bottom-up refit: the second thread to arrive at a node merges its two children and moves on
 __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__restrict__ tv, int N, float pad,
                         const int2 *__restrict__ children, const int *__restrict__ parent, float *__restrict__ box /* (2N-1) x 6 */,
-                        int *__restrict__ flags) {
+                        int *__restrict__ flags, float4 *__restrict__ tribox) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     int tri = (int)(uint32_t)keys[p];
@@ -139,6 +139,8 @@ __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__res
     lo[2] = fminf(t.a.z, fminf(t.b.z, t.c.z)) - pad; hi[2] = fmaxf(t.a.z, fmaxf(t.b.z, t.c.z)) + pad;
     size_t self = (size_t)(N - 1) + p;
     for (int d = 0; d < 3; d++) { box[self * 6 + d] = lo[d]; box[self * 6 + 3 + d] = hi[d]; }
+    tribox[2 * (size_t)tri] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    tribox[2 * (size_t)tri + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
     if (N == 1) return;
     __threadfence();
     int node = parent[self];
@@ -186,6 +188,7 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     DZ_CUDA(cudaEventRecord(e0, st));
     DZ_CUDA(cudaMalloc(&ctx->d_triverts, sizeof(TriVerts) * (size_t)(N > 0 ? N : 1)));
     DZ_CUDA(cudaMalloc(&ctx->d_nodes, sizeof(BvhNode) * (size_t)(N > 1 ? N - 1 : 1)));
+    DZ_CUDA(cudaMalloc(&ctx->d_tribox, sizeof(float4) * 2 * (size_t)(N > 0 ? N : 1)));
     if (N == 0) { ctx->root = 0; DZ_CUDA(cudaEventDestroy(e0)); DZ_CUDA(cudaEventDestroy(e1)); return DAISY_OK; }
     int npad = BITONIC_BLOCK;
     while (npad < N) npad <<= 1;
@@ -208,7 +211,7 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     if (N > 1) {
         k_hierarchy<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_parent);
     }
-    k_refit<<<(N + 255) / 256, 256, 0, st>>>(d_keys, ctx->d_triverts, N, ctx->pad, d_children, d_parent, d_box, d_flags);
+    k_refit<<<(N + 255) / 256, 256, 0, st>>>(d_keys, ctx->d_triverts, N, ctx->pad, d_children, d_parent, d_box, d_flags, ctx->d_tribox);
     if (N > 1) {
         k_pack_nodes<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_box, ctx->d_nodes);
         ctx->root = 0;

@@ -144,6 +144,7 @@ struct daisy_ctx {
     float *d_vertices = nullptr, *d_normals = nullptr;
     int *d_tri = nullptr;
     TriVerts *d_triverts = nullptr;
+    float4 *d_tribox = nullptr; // padded per-triangle boxes (2 float4 each), same boxes as the LBVH leaves
     PatchGeom *d_geom = nullptr;
     // LBVH
     BvhNode *d_nodes = nullptr;
@@ -154,7 +155,7 @@ struct daisy_ctx {
     float *d_F = nullptr; // (row1-row0) x ldF
     int64_t ldF = 0;
     bool have_F = false;
-    int64_t pairs_traced = 0, pairs_owned = 0;
+    int64_t pairs_traced = 0, pairs_owned = 0, pairs_heavy = 0;
     double ff_ms = 0.0;
     int num_sms = 148;
 };

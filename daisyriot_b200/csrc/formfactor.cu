@@ -189,10 +189,170 @@ __device__ __forceinline__ bool ray_sees(const BvhNode *__restrict__ nodes, cons
     return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Shaft culling (Haines & Wallace style) per patch pair.  Every visibility ray of the pair (lo -> hi) lies inside
+// the convex hull of the two triangles, so a triangle can only be hit by one of those rays if its (padded) box meets
+// that hull.  The hull is tested conservatively with six separating axes: x, y, z and D x {x,y,z} with D the
+// direction between the two centroids.  Skipping any axis only makes the test say "may intersect" more often, so the
+// candidate list is always a superset of the triangles any of the S rays can touch; rays are then tested against the
+// list with the very same watertight routine and the same (t, id) rule => identical masks, far fewer node visits.
+#define FF_QCAP 8 // pending watertight tests per lane
+#define SHAFT_CAP 256 // ints of global scratch per pair slot; longer lists fall back to per-ray LBVH walks
+struct Shaft {
+    float lox, loy, loz, hix, hiy, hiz; // hull AABB
+    float Dx, Dy, Dz;                   // centroid(hi) - centroid(lo) (scaled by 3, irrelevant)
+    float c0min, c0max, c1min, c1max, c2min, c2max; // hull extent along D x e_x, D x e_y, D x e_z
+};
+
+__device__ __forceinline__ Shaft make_shaft(const TriVerts &A, const TriVerts &B) {
+    Shaft s;
+    float4 p[6] = { A.a, A.b, A.c, B.a, B.b, B.c };
+    s.lox = s.hix = p[0].x; s.loy = s.hiy = p[0].y; s.loz = s.hiz = p[0].z;
+#pragma unroll
+    for (int i = 1; i < 6; i++) {
+        s.lox = fminf(s.lox, p[i].x); s.hix = fmaxf(s.hix, p[i].x);
+        s.loy = fminf(s.loy, p[i].y); s.hiy = fmaxf(s.hiy, p[i].y);
+        s.loz = fminf(s.loz, p[i].z); s.hiz = fmaxf(s.hiz, p[i].z);
+    }
+    s.Dx = (B.a.x + B.b.x + B.c.x) - (A.a.x + A.b.x + A.c.x);
+    s.Dy = (B.a.y + B.b.y + B.c.y) - (A.a.y + A.b.y + A.c.y);
+    s.Dz = (B.a.z + B.b.z + B.c.z) - (A.a.z + A.b.z + A.c.z);
+    s.c0min = s.c1min = s.c2min = INFINITY;
+    s.c0max = s.c1max = s.c2max = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float q0 = p[i].y * s.Dz - p[i].z * s.Dy;
+        float q1 = p[i].z * s.Dx - p[i].x * s.Dz;
+        float q2 = p[i].x * s.Dy - p[i].y * s.Dx;
+        s.c0min = fminf(s.c0min, q0); s.c0max = fmaxf(s.c0max, q0);
+        s.c1min = fminf(s.c1min, q1); s.c1max = fmaxf(s.c1max, q1);
+        s.c2min = fminf(s.c2min, q2); s.c2max = fmaxf(s.c2max, q2);
+    }
+    return s;
+}
+
+// conservative: false only if one of the six axes separates the (padded) box from the hull
+__device__ __forceinline__ bool shaft_box(const Shaft &s, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    if (lox > s.hix || hix < s.lox || loy > s.hiy || hiy < s.loy || loz > s.hiz || hiz < s.loz) return false;
+    float cx = 0.5f * (lox + hix), cy = 0.5f * (loy + hiy), cz = 0.5f * (loz + hiz);
+    float hx = 0.5f * (hix - lox), hy = 0.5f * (hiy - loy), hz = 0.5f * (hiz - loz);
+    float ax = fabsf(s.Dx), ay = fabsf(s.Dy), az = fabsf(s.Dz);
+    // slack: a few ulps of the projected magnitudes, on top of the 1e-4*extent padding the boxes already carry
+    float p0 = cy * s.Dz - cz * s.Dy, r0 = hy * az + hz * ay;
+    r0 += 1e-5f * (fabsf(p0) + r0);
+    if (p0 - r0 > s.c0max || p0 + r0 < s.c0min) return false;
+    float p1 = cz * s.Dx - cx * s.Dz, r1 = hz * ax + hx * az;
+    r1 += 1e-5f * (fabsf(p1) + r1);
+    if (p1 - r1 > s.c1max || p1 + r1 < s.c1min) return false;
+    float p2 = cx * s.Dy - cy * s.Dx, r2 = hx * ay + hy * ax;
+    r2 += 1e-5f * (fabsf(p2) + r2);
+    if (p2 - r2 > s.c2max || p2 + r2 < s.c2min) return false;
+    return true;
+}
+
+// collect the triangles (other than lo and hi) whose leaf box meets the shaft; returns -1 if more than SHAFT_CAP
+__device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, int root, const Shaft &sh, int lo, int hi, int *__restrict__ cand) {
+    int n = 0;
+    int stack[64];
+    int sp = 0;
+    int cur = root;
+    while (true) {
+        if (cur < 0) {
+            int k = ~cur;
+            if (k != lo && k != hi) {
+                if (n == SHAFT_CAP) return -1;
+                cand[n++] = k;
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+            continue;
+        }
+        BvhNode nd = nodes[cur];
+        bool hl = shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
+        bool hr = shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
+        if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
+        else if (hl) cur = nd.d.x;
+        else if (hr) cur = nd.d.y;
+        else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return n;
+}
+
+// Visibility mask of one pair with the whole warp: lane = sample, the candidate list is walked in lock step (uniform
+// loads), each candidate first meets a cheap conservative slab test against its padded box and only then the
+// watertight test.  Same predicate as ray_sees: sample i sees hi iff hi is accepted at t_hi and no other triangle k
+// is accepted with (t_k, k) < (t_hi, hi); lo takes part like any other triangle.
+__device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox,
+                                                   const TriVerts &Tlo, const TriVerts &Thi, int hi, const int *cand,
+                                                   int ncand, const float *s_uv, int S, int lane, int *wq) {
+    uint64_t mask = 0;
+    for (int pass = 0; pass * 32 < S; pass++) {
+        const int i = pass * 32 + lane;
+        const int ii = min(i, S - 1);
+        const float u = s_uv[2 * ii], v = s_uv[2 * ii + 1];
+        f3 a0 = xyz(Tlo.a), a1 = xyz(Thi.a);
+        f3 org = e_add(e_add(a0, e_scale(e_sub(xyz(Tlo.b), a0), u)), e_scale(e_sub(xyz(Tlo.c), a0), v));
+        f3 dst = e_add(e_add(a1, e_scale(e_sub(xyz(Thi.b), a1), u)), e_scale(e_sub(xyz(Thi.c), a1), v));
+        f3 dir = e_normalize(e_sub(dst, org));
+        f3 o = e_add(org, e_scale(dir, 0.000001f));
+        WRay w = wray_setup(o, dir);
+        float thi = 0.f, uu, vv, tk;
+        bool alive = (i < S) && wray_tri(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv);
+        if (alive && wray_tri(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) alive = false;
+        f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+        // Slab tests run in lock step over the list (uniform box loads); a lane that passes one only QUEUES the
+        // triangle.  The expensive watertight tests are then issued for whole queues at a time, so a warp instruction
+        // slot is spent on them only when many lanes have one pending, not whenever a single lane does.
+        int qlen = 0;
+        auto flush = [&]() {
+            for (int t = 0; t < FF_QCAP; t++) {
+                if (!__any_sync(0xffffffffu, alive && t < qlen)) break;
+                if (alive && t < qlen) {
+                    const int k = wq[t * 32 + lane];
+                    TriVerts tr = tv[k];
+                    if (wray_tri(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) alive = false;
+                }
+            }
+            qlen = 0;
+        };
+        bool any_alive = __any_sync(0xffffffffu, alive);
+        for (int c0 = 0; c0 < ncand && any_alive; c0 += 32) {
+            // the list was written by another lane of this warp: read it through L2 (ld.global.cg), 32 ids at a time
+            const int kk = (c0 + lane < ncand) ? __ldcg(cand + c0 + lane) : 0;
+            const int nb = min(32, ncand - c0);
+            int kn = __shfl_sync(0xffffffffu, kk, 0);
+            float4 b0n = tribox[2 * (size_t)kn], b1n = tribox[2 * (size_t)kn + 1];
+            for (int j = 0; j < nb; j++) {
+                const int k = kn;
+                const float4 b0 = b0n, b1 = b1n;
+                if (j + 1 < nb) { // fetch the next box while this one is tested
+                    kn = __shfl_sync(0xffffffffu, kk, j + 1);
+                    b0n = tribox[2 * (size_t)kn]; b1n = tribox[2 * (size_t)kn + 1];
+                }
+                float tn;
+                if (alive && ray_box(o, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi, tn)) { wq[qlen * 32 + lane] = k; qlen++; }
+                if (__any_sync(0xffffffffu, qlen == FF_QCAP)) {
+                    flush();
+                    any_alive = __any_sync(0xffffffffu, alive);
+                    if (!any_alive) break;
+                }
+            }
+        }
+        if (any_alive) flush();
+        mask |= (uint64_t)__ballot_sync(0xffffffffu, alive) << (32 * pass);
+    }
+    return mask;
+}
+
 struct FFParams {
     const PatchGeom *geom;
     const TriVerts *tv;
     const BvhNode *nodes;
+    const float4 *tribox; // padded triangle boxes, 2 float4 per triangle
+    int *scratch;         // gridDim.x * FF_THREADS * SHAFT_CAP candidate slots
     int root, N, S;
     int row0, row1;      // rows this context owns
     float *F;            // (row1-row0) x ldF, may be null (mask-only run)
@@ -201,7 +361,7 @@ struct FFParams {
     int mrow0, mrow1;
     int ntiles;          // tiles per side
     int *job_counter;    // dynamic tile scheduler
-    unsigned long long *pair_counter; // [0] pairs traced by this context, [1] of those, pairs whose lower index it owns
+    unsigned long long *pair_counter; // [0] pairs traced by this context, [1] of those, pairs whose lower index it owns, [2] pairs that fell back to per-ray LBVH walks
     int njobs;
     const int2 *jobs;    // (row tile, col tile), col tile >= row tile
 };
@@ -212,7 +372,10 @@ struct FFSmem {
     float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
     float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
     unsigned short list[TILE * TILE];
-    int nlist, next, job, nown;
+    unsigned short heavy[TILE * TILE];
+    int nlist, next, job, nown, nheavy, hnext;
+    float uv[2 * DAISY_MAX_SAMPLES];
+    int wq[FF_THREADS / 32][FF_QCAP * 32];
 };
 
 template <int VARIANT>
@@ -224,9 +387,13 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
     float(*s_rc)[TILE + 1] = sm.rc;
     float(*s_cr)[TILE + 1] = sm.cr;
     unsigned short *s_list = sm.list;
-    int &s_nlist = sm.nlist, &s_next = sm.next, &s_job = sm.job, &s_nown = sm.nown;
+    int &s_nlist = sm.nlist, &s_next = sm.next, &s_job = sm.job, &s_nown = sm.nown, &s_nheavy = sm.nheavy, &s_hnext = sm.hnext;
+    unsigned short *s_heavy = sm.heavy;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    if (tid < 2 * DAISY_MAX_SAMPLES) sm.uv[tid] = c_uv[tid];
+    int *my_cand = P.scratch + ((size_t)blockIdx.x * FF_THREADS + tid) * SHAFT_CAP;
+    int *warp_cand = P.scratch + ((size_t)blockIdx.x * FF_THREADS + (tid & ~31)) * SHAFT_CAP;
 
     while (true) {
         if (tid == 0) s_job = atomicAdd(P.job_counter, 1);
@@ -236,7 +403,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
         int2 jt = P.jobs[job];
         const int R0 = jt.x * TILE, C0 = jt.y * TILE;
         const bool diag = (jt.x == jt.y);
-        if (tid == 0) { s_nlist = 0; s_next = 0; s_nown = 0; }
+        if (tid == 0) { s_nlist = 0; s_next = 0; s_nown = 0; s_nheavy = 0; s_hnext = 0; }
         // stage the two patch groups (float4-granular copies: 5 + 3 float4 per patch)
         for (int i = tid; i < TILE * 5; i += FF_THREADS) {
             int p = i / 5, q = i - p * 5;
@@ -288,42 +455,76 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
         const int nlist = s_nlist;
         if (tid == 0 && nlist) { atomicAdd(P.pair_counter, (unsigned long long)nlist); atomicAdd(P.pair_counter + 1, (unsigned long long)s_nown); }
 
-        // ---- phase 2: S visibility rays per listed pair; a warp claims 32 pairs at a time, lane = pair,
-        // all lanes trace sample i together (neighbouring pairs + same sample => coherent rays)
-        while (true) {
+        // ---- phase 2: S visibility rays per listed pair; a warp claims 32 pairs at a time, lane = pair, all lanes
+        // trace sample i together (neighbouring pairs + same sample => coherent rays).  First every pair gets a
+        // shaft candidate list; pairs whose list fits are resolved against it (2a), the rest walk the LBVH per ray (2b).
+        auto finish_pair = [&](int rl, int cl, int r, int c, uint64_t mask) {
+            // visibility = (#hits as float) / RAYS_PER_PATCH                 OptixPrimeFunctionality.cpp:206-211
+            float visibility = fd((float)__popcll(mask), (float)P.S);
+            float f_rc, f_cr;
+            if (VARIANT == DAISY_FF_DEVICE) {
+                // Tripl(row, col, visibility * m_value): float*double in double; setFromTriplets casts to float
+                f_rc = __double2float_rn(__dmul_rn((double)visibility, (double)s_rc[rl][cl]));
+                f_cr = __double2float_rn(__dmul_rn((double)visibility, (double)s_cr[cl][rl]));
+            } else {
+                // p2pFormfactor returns formfactor*visibility (float); mirrored entry by reciprocity      :165,:343
+                f_rc = fm(s_rc[rl][cl], visibility);
+                f_cr = (f_rc > 0.0f) ? fd(fm(s_gr[rl].n.w, f_rc), s_gc[cl].n.w) : 0.0f;
+            }
+            if (mask == 0) { f_rc = 0.0f; f_cr = 0.0f; }
+            s_rc[rl][cl] = f_rc;
+            s_cr[cl][rl] = f_cr;
+            if (P.masks) {
+                if (r >= P.mrow0 && r < P.mrow1) P.masks[(size_t)(r - P.mrow0) * P.N + c] = mask;
+                if (c >= P.mrow0 && c < P.mrow1) P.masks[(size_t)(c - P.mrow0) * P.N + r] = mask;
+            }
+        };
+        while (true) { // 2a
             int q0 = 0;
             if (lane == 0) q0 = atomicAdd(&s_next, 32);
             q0 = __shfl_sync(0xffffffffu, q0, 0);
             if (q0 >= nlist) break;
-            int q = q0 + lane;
+            // (i) lane = pair: shaft walk, candidates into this lane's global scratch slot
+            const int q = q0 + lane;
+            int idx = 0, ncand = -2;
             if (q < nlist) {
-                int idx = s_list[q];
+                idx = s_list[q];
+                int rl = idx >> 6, cl = idx & 63;
+                Shaft sh = make_shaft(s_tr[rl], s_tc[cl]);
+                ncand = shaft_candidates(P.nodes, P.root, sh, R0 + rl, C0 + cl, my_cand);
+                if (ncand < 0) s_heavy[atomicAdd(&s_nheavy, 1)] = (unsigned short)idx;
+            }
+            __syncwarp();
+            // (ii) lane = sample: the warp resolves its 32 pairs one after the other
+            for (int j = 0; j < 32; j++) {
+                const int nc = __shfl_sync(0xffffffffu, ncand, j);
+                if (nc < 0) continue;
+                const int idj = __shfl_sync(0xffffffffu, idx, j);
+                const int rl = idj >> 6, cl = idj & 63;
+                const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
+                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc, sm.uv, P.S, lane, sm.wq[tid >> 5]);
+                if (lane == 0) finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        const int nheavy = s_nheavy;
+        if (tid == 0 && nheavy) atomicAdd(P.pair_counter + 2, (unsigned long long)nheavy);
+        while (true) { // 2b
+            int q0 = 0;
+            if (lane == 0) q0 = atomicAdd(&s_hnext, 32);
+            q0 = __shfl_sync(0xffffffffu, q0, 0);
+            if (q0 >= nheavy) break;
+            int q = q0 + lane;
+            if (q < nheavy) {
+                int idx = s_heavy[q];
                 int rl = idx >> 6, cl = idx & 63;
                 int r = R0 + rl, c = C0 + cl;
                 const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
                 uint64_t mask = 0;
-                for (int i = 0; i < P.S; i++) {
+                for (int i = 0; i < P.S; i++)
                     if (ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, r, c, c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << i);
-                }
-                // visibility = (#hits as float) / RAYS_PER_PATCH                 OptixPrimeFunctionality.cpp:206-211
-                float visibility = fd((float)__popcll(mask), (float)P.S);
-                float f_rc, f_cr;
-                if (VARIANT == DAISY_FF_DEVICE) {
-                    // Tripl(row, col, visibility * m_value): float*double in double; setFromTriplets casts to float
-                    f_rc = __double2float_rn(__dmul_rn((double)visibility, (double)s_rc[rl][cl]));
-                    f_cr = __double2float_rn(__dmul_rn((double)visibility, (double)s_cr[cl][rl]));
-                } else {
-                    // p2pFormfactor returns formfactor*visibility (float); mirrored entry by reciprocity      :165,:343
-                    f_rc = fm(s_rc[rl][cl], visibility);
-                    f_cr = (f_rc > 0.0f) ? fd(fm(s_gr[rl].n.w, f_rc), s_gc[cl].n.w) : 0.0f;
-                }
-                if (mask == 0) { f_rc = 0.0f; f_cr = 0.0f; }
-                s_rc[rl][cl] = f_rc;
-                s_cr[cl][rl] = f_cr;
-                if (P.masks) {
-                    if (r >= P.mrow0 && r < P.mrow1) P.masks[(size_t)(r - P.mrow0) * P.N + c] = mask;
-                    if (c >= P.mrow0 && c < P.mrow1) P.masks[(size_t)(c - P.mrow0) * P.N + r] = mask;
-                }
+                finish_pair(rl, cl, r, c, mask);
             }
         }
         __syncthreads();
@@ -375,12 +576,12 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     unsigned long long *d_pairs = nullptr;
     DZ_CUDA(cudaMalloc(&d_jobs, sizeof(int2) * (njobs ? njobs : 1)));
     DZ_CUDA(cudaMalloc(&d_counter, sizeof(int)));
-    DZ_CUDA(cudaMalloc(&d_pairs, 2 * sizeof(unsigned long long)));
+    DZ_CUDA(cudaMalloc(&d_pairs, 3 * sizeof(unsigned long long)));
     DZ_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(int2) * njobs, cudaMemcpyHostToDevice, st));
     DZ_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
-    DZ_CUDA(cudaMemsetAsync(d_pairs, 0, 2 * sizeof(unsigned long long), st));
+    DZ_CUDA(cudaMemsetAsync(d_pairs, 0, 3 * sizeof(unsigned long long), st));
     FFParams P;
-    P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
+    P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.tribox = ctx->d_tribox; P.scratch = nullptr; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
     P.masks = d_masks; P.mrow0 = mrow0; P.mrow1 = mrow1;
@@ -397,19 +598,22 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int grid = ctx->num_sms * blocks_per_sm; // persistent CTAs, a multiple of the SM count
     if ((size_t)grid > njobs) grid = (int)njobs;
+    int *d_scratch = nullptr;
+    DZ_CUDA(cudaMalloc(&d_scratch, sizeof(int) * (size_t)grid * FF_THREADS * SHAFT_CAP));
+    P.scratch = d_scratch;
     DZ_CUDA(cudaEventRecord(e0, st));
     if (variant == DAISY_FF_DEVICE) k_ff_tiles<DAISY_FF_DEVICE><<<grid, FF_THREADS, smem, st>>>(P);
     else k_ff_tiles<DAISY_FF_HOST><<<grid, FF_THREADS, smem, st>>>(P);
     DZ_CUDA(cudaGetLastError());
     DZ_CUDA(cudaEventRecord(e1, st));
-    unsigned long long pairs[2] = { 0, 0 };
+    unsigned long long pairs[3] = { 0, 0, 0 };
     DZ_CUDA(cudaMemcpyAsync(pairs, d_pairs, sizeof(pairs), cudaMemcpyDeviceToHost, st));
     DZ_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    if (write_F) { ctx->ff_ms = ms; ctx->pairs_traced = (int64_t)pairs[0]; ctx->pairs_owned = (int64_t)pairs[1]; }
+    if (write_F) { ctx->ff_ms = ms; ctx->pairs_traced = (int64_t)pairs[0]; ctx->pairs_owned = (int64_t)pairs[1]; ctx->pairs_heavy = (int64_t)pairs[2]; }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_jobs); cudaFree(d_counter); cudaFree(d_pairs);
+    cudaFree(d_jobs); cudaFree(d_counter); cudaFree(d_pairs); cudaFree(d_scratch);
     free(h_jobs);
     return DAISY_OK;
 }

@@ -97,6 +97,9 @@ int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int nrows, uin
 int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *pairs_owned, int64_t *rays, double *lbvh_ms,
                             double *ff_ms);
 
+/* diagnostic: pairs of the last build whose shaft candidate list overflowed and were traced by per-ray LBVH walks */
+int64_t daisy_formfactors_pairs_fallback(daisy_ctx *ctx);
+
 /* ---- radiosity / fluorescence gather ------------------------------------------------------------------------
  * replaces the Lightning family (VS/Lightning.h): residual <- M (F residual); B += residual
  *   K=1, M=[1]            : BWLightning       (:386-443)

@@ -21,7 +21,7 @@ for N in sizes:
     t2 = time.time()
     st = p.stats()
     print(f"N={N} ctx {t1-t:.3f}s lbvh {st['lbvh_ms']:.2f}ms ff {st['ff_ms']:.1f}ms wall {t2-t1:.3f}s pairs {st['pairs_traced']} "
-          f"({st['pairs_traced']/(N*(N-1)/2):.3f}) rays/s {st['rays']/(st['ff_ms']*1e-3):.3e}", flush=True)
+          f"({st['pairs_traced']/(N*(N-1)/2):.3f}) fallback {st['pairs_fallback']/max(1,st['pairs_traced']):.3f} rays/s {st['rays']/(st['ff_ms']*1e-3):.3e}", flush=True)
     for K in (9, 3, 1, 32):
         rng = np.random.RandomState(0)
         E = rng.uniform(0, 1, (K, N)).astype(np.float32)
