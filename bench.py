@@ -243,7 +243,10 @@ def run_ours(args):
     t0 = time.time()
     mesh = dz.MeshS.from_scene(sc)
     optixP = dz.OptixPrimeFunctionality(mesh, device=local, rands=uv, rank=rank, nranks=world)
-    optixP.cudaCalculateRadiosityMatrix()
+    if world > 1:
+        ddist.build_formfactors_sharded(optixP, peer_tiles=not args.no_peer_tiles)  # mirrored tiles go to the peer's F over NVLink
+    else:
+        optixP.cudaCalculateRadiosityMatrix()
     torch.cuda.synchronize()
     ff_wall = allmax(time.time() - t0)
     st = optixP.stats()
@@ -378,6 +381,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DAISY_WORKLOAD", "cornell_128k"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU form-factor sampling for the baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-tiles", action="store_true", help="multi-GPU: trace every tile touching this rank's rows instead of exchanging mirrored tiles")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

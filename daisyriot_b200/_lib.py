@@ -51,6 +51,9 @@ SYMBOLS = {
     "daisy_formfactors_write_rows": (_i, [_vp, _i, _i, _fp]),
     "daisy_visibility_masks": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_uint64)]),
     "daisy_formfactors_stats": (_i, [_vp, _i64p, _i64p, _i64p, _dp, _dp]),
+    "daisy_formfactors_alloc": (_i, [_vp]),
+    "daisy_formfactors_ipc_handle": (_i, [_vp, _vp]),
+    "daisy_formfactors_set_peers": (_i, [_vp, _vp, _i]),
     "daisy_formfactors_pairs_fallback": (C.c_int64, [_vp]),
     "daisy_solver_create": (_i, [_vp, _i, _fp, _fp, _i, _ip, C.POINTER(_vp)]),
     "daisy_solver_destroy": (None, [_vp]),

@@ -26,6 +26,9 @@ extern "C" int daisy_device_count(void) {
 
 static void free_ctx(daisy_ctx *c) {
     if (!c) return;
+    if (c->peers_set)
+        for (int g = 0; g < c->nranks && g < 16; g++)
+            if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
     cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom);
     cudaFree(c->d_nodes); cudaFree(c->d_F);
     delete c;
@@ -208,6 +211,45 @@ extern "C" int daisy_formfactors_build(daisy_ctx *ctx, int variant) {
     rc = dz_build_formfactors(ctx, variant, nullptr, 0, 0, true);
     if (rc) return rc;
     ctx->have_F = true;
+    return DAISY_OK;
+}
+
+// ---- multi-GPU: mirrored tiles are written straight into the owning rank's matrix over NVLink -------------------
+extern "C" int daisy_formfactors_alloc(daisy_ctx *ctx) {
+    DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_formfactors_alloc: null context");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_F(ctx);
+    if (rc) return rc;
+    DZ_CUDA(cudaStreamSynchronize(ctx->stream)); // the zero fill must be complete before any peer may write
+    return DAISY_OK;
+}
+
+extern "C" int daisy_formfactors_ipc_handle(daisy_ctx *ctx, void *handle64) {
+    DZ_REQUIRE(ctx && handle64, DAISY_E_INVALID, "daisy_formfactors_ipc_handle: null argument");
+    DZ_REQUIRE(ctx->d_F, DAISY_E_STATE, "daisy_formfactors_ipc_handle: call daisy_formfactors_alloc first");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    DZ_CUDA(cudaIpcGetMemHandle(&h, ctx->d_F));
+    memcpy(handle64, &h, 64);
+    return DAISY_OK;
+}
+
+extern "C" int daisy_formfactors_set_peers(daisy_ctx *ctx, const void *handles, int nranks) {
+    DZ_REQUIRE(ctx && handles, DAISY_E_INVALID, "daisy_formfactors_set_peers: null argument");
+    DZ_REQUIRE(nranks == ctx->nranks && nranks <= 16, DAISY_E_INVALID, "daisy_formfactors_set_peers: nranks must match the partition (<= 16)");
+    DZ_REQUIRE(ctx->d_F && !ctx->peers_set, DAISY_E_STATE, "daisy_formfactors_set_peers: allocate first, set once");
+    DZ_REQUIRE(ctx->rows_per_rank % 64 == 0, DAISY_E_STATE, "daisy_formfactors_set_peers: rows per rank must be a multiple of the tile size");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    for (int g = 0; g < nranks; g++) {
+        if (g == ctx->rank) { ctx->peerF[g] = ctx->d_F; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * (size_t)g, 64);
+        void *p = nullptr;
+        DZ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peerF[g] = (float *)p;
+    }
+    ctx->peers_set = true;
     return DAISY_OK;
 }
 

@@ -155,6 +155,8 @@ struct daisy_ctx {
     float *d_F = nullptr; // (row1-row0) x ldF
     int64_t ldF = 0;
     bool have_F = false;
+    float *peerF[16] = { nullptr }; // every rank's F (own pointer or CUDA-IPC mapping), set by daisy_formfactors_set_peers
+    bool peers_set = false;
     int64_t pairs_traced = 0, pairs_owned = 0, pairs_heavy = 0;
     double ff_ms = 0.0;
     int num_sms = 148;

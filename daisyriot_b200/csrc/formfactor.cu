@@ -357,6 +357,11 @@ struct FFParams {
     int row0, row1;      // rows this context owns
     float *F;            // (row1-row0) x ldF, may be null (mask-only run)
     int64_t ldF;
+    // peer mode (multi-GPU): every upper-triangle tile is computed by exactly one rank, which stores the tile into the
+    // row owner's F and the mirrored tile into the column owner's F -- its own memory or a peer's, mapped through CUDA
+    // IPC and written over NVLink
+    int peer_mode, n_per_rank;
+    float *Fpeer[16];
     uint64_t *masks;     // optional (mrow1-mrow0) x N
     int mrow0, mrow1;
     int ntiles;          // tiles per side
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
             int rl = idx >> 6, cl = idx & 63;
             int r = R0 + rl, c = C0 + cl;
             bool valid = (r < P.N) && (c < P.N) && (r < c) &&
-                         ((r >= P.row0 && r < P.row1) || (c >= P.row0 && c < P.row1));
+                         (P.peer_mode || (r >= P.row0 && r < P.row1) || (c >= P.row0 && c < P.row1));
             float f_rc = 0.0f, f_cr = 0.0f;
             bool trace = false;
             if (valid) {
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
             s_rc[rl][cl] = f_rc;
             s_cr[cl][rl] = f_cr;
             unsigned m = __ballot_sync(0xffffffffu, trace);
-            unsigned mo = __ballot_sync(0xffffffffu, trace && r >= P.row0 && r < P.row1);
+            unsigned mo = __ballot_sync(0xffffffffu, trace && (P.peer_mode || (r >= P.row0 && r < P.row1)));
             if (mo && lane == 0) atomicAdd(&s_nown, __popc(mo));
             if (m) {
                 int base = 0;
@@ -530,7 +535,23 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
         __syncthreads();
 
         // ---- phase 3: coalesced tile stores.  Rows of s_rc are rows R0.. of F; rows of s_cr are rows C0.. of F.
-        if (P.F) {
+        if (P.F && P.peer_mode) {
+            const int ga = R0 / P.n_per_rank, gb = C0 / P.n_per_rank; // tiles never straddle two ranks (n is a multiple of 128)
+            float *Fa = P.Fpeer[ga] - (size_t)ga * P.n_per_rank * P.ldF;
+            float *Fb = P.Fpeer[gb] - (size_t)gb * P.n_per_rank * P.ldF;
+            for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
+                int a = idx >> 6, b = idx & 63;
+                if (diag) {
+                    int r = R0 + a, c = C0 + b;
+                    if (r < P.N && c < P.N) Fa[(size_t)r * P.ldF + c] = (a < b) ? s_rc[a][b] : ((a > b) ? s_cr[a][b] : 0.0f);
+                } else {
+                    int r = R0 + a, c = C0 + b;
+                    if (r < P.N && c < P.N) Fa[(size_t)r * P.ldF + c] = s_rc[a][b];
+                    int r2 = C0 + a, c2 = R0 + b; // mirrored tile: row = column patch
+                    if (r2 < P.N && c2 < P.N) Fb[(size_t)r2 * P.ldF + c2] = s_cr[a][b];
+                }
+            }
+        } else if (P.F) {
             for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
                 int a = idx >> 6, b = idx & 63;
                 if (diag) {
@@ -558,19 +579,30 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     const int ntiles = (N + TILE - 1) / TILE;
     // row range of interest: the context's rows when writing F, else the mask rows
     int r0 = write_F ? ctx->row0 : mrow0, r1 = write_F ? ctx->row1 : mrow1;
-    if (r1 <= r0) return DAISY_OK;
+    if (r1 <= r0 && !(write_F && ctx->peers_set)) return DAISY_OK;
     int t0 = r0 / TILE, t1 = (r1 - 1) / TILE; // tiles overlapping the range
-    // jobs: upper-triangle tiles (R <= C) with R or C inside [t0, t1]
+    // jobs: upper-triangle tiles (R <= C).  Local mode: every tile with R or C inside this context's rows [t0, t1]
+    // (off-diagonal blocks are then traced by both owners).  Peer mode: every tile is assigned to exactly one rank --
+    // tiles inside one rank's block to that rank, tiles between ranks a < b alternately to a and b (checkerboard).
+    const bool peer = write_F && ctx->peers_set && ctx->nranks > 1;
+    const int tiles_per_rank = ctx->rows_per_rank / TILE;
+    auto mine = [&](int R, int C) -> bool {
+        if (!peer) return (R >= t0 && R <= t1) || (C >= t0 && C <= t1);
+        int a = R / tiles_per_rank, b = C / tiles_per_rank;
+        if (a == b) return a == ctx->rank;
+        if (a != ctx->rank && b != ctx->rank) return false;
+        return (((R + C) & 1) == 0) ? (ctx->rank == a) : (ctx->rank == b);
+    };
     size_t njobs = 0;
     for (int R = 0; R < ntiles; R++)
         for (int C = R; C < ntiles; C++)
-            if ((R >= t0 && R <= t1) || (C >= t0 && C <= t1)) njobs++;
+            if (mine(R, C)) njobs++;
     int2 *h_jobs = (int2 *)malloc(sizeof(int2) * (njobs ? njobs : 1));
     if (!h_jobs) { daisy_set_error("out of host memory for the tile list"); return DAISY_E_NOMEM; }
     size_t k = 0;
     for (int R = 0; R < ntiles; R++)
         for (int C = R; C < ntiles; C++)
-            if ((R >= t0 && R <= t1) || (C >= t0 && C <= t1)) h_jobs[k++] = make_int2(R, C);
+            if (mine(R, C)) h_jobs[k++] = make_int2(R, C);
     int2 *d_jobs = nullptr;
     int *d_counter = nullptr;
     unsigned long long *d_pairs = nullptr;
@@ -584,6 +616,8 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.tribox = ctx->d_tribox; P.scratch = nullptr; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
+    P.peer_mode = peer ? 1 : 0; P.n_per_rank = ctx->rows_per_rank;
+    for (int g = 0; g < 16; g++) P.Fpeer[g] = (peer && g < ctx->nranks) ? ctx->peerF[g] : nullptr;
     P.masks = d_masks; P.mrow0 = mrow0; P.mrow1 = mrow1;
     P.ntiles = ntiles; P.job_counter = d_counter; P.pair_counter = d_pairs; P.njobs = (int)njobs; P.jobs = d_jobs;
     cudaEvent_t e0, e1;
@@ -599,11 +633,13 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     int grid = ctx->num_sms * blocks_per_sm; // persistent CTAs, a multiple of the SM count
     if ((size_t)grid > njobs) grid = (int)njobs;
     int *d_scratch = nullptr;
-    DZ_CUDA(cudaMalloc(&d_scratch, sizeof(int) * (size_t)grid * FF_THREADS * SHAFT_CAP));
+    DZ_CUDA(cudaMalloc(&d_scratch, sizeof(int) * (size_t)(grid > 0 ? grid : 1) * FF_THREADS * SHAFT_CAP));
     P.scratch = d_scratch;
     DZ_CUDA(cudaEventRecord(e0, st));
-    if (variant == DAISY_FF_DEVICE) k_ff_tiles<DAISY_FF_DEVICE><<<grid, FF_THREADS, smem, st>>>(P);
-    else k_ff_tiles<DAISY_FF_HOST><<<grid, FF_THREADS, smem, st>>>(P);
+    if (grid > 0) {
+        if (variant == DAISY_FF_DEVICE) k_ff_tiles<DAISY_FF_DEVICE><<<grid, FF_THREADS, smem, st>>>(P);
+        else k_ff_tiles<DAISY_FF_HOST><<<grid, FF_THREADS, smem, st>>>(P);
+    }
     DZ_CUDA(cudaGetLastError());
     DZ_CUDA(cudaEventRecord(e1, st));
     unsigned long long pairs[3] = { 0, 0, 0 };

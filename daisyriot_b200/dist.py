@@ -57,6 +57,30 @@ def total_band_sums(buffer_f32, K: int, K_padded: int, n: int, nranks: int) -> n
     return out
 
 
+def build_formfactors_sharded(optixP, variant: int = _lib.FF_DEVICE, group=None, peer_tiles: bool = True):
+    """Row-sharded form-factor build on every rank of ``group``.
+
+    ``peer_tiles=True``: CUDA-IPC handles of every rank's matrix are exchanged once, each upper-triangle tile is then
+    traced by exactly one rank and its mirror is stored into the peer's matrix over NVLink (no ray is traced twice).
+    ``peer_tiles=False``: no exchange at all; each rank traces every tile touching its rows."""
+    import torch
+    import torch.distributed as tdist
+    L = _lib.lib()
+    world = optixP.nranks
+    if world > 1 and peer_tiles:
+        _lib.check(L.daisy_formfactors_alloc(optixP._ctx), "formfactors_alloc")
+        h = C.create_string_buffer(64)
+        _lib.check(L.daisy_formfactors_ipc_handle(optixP._ctx, h), "formfactors_ipc_handle")
+        handles = [None] * world
+        tdist.all_gather_object(handles, bytes(h.raw), group=group)
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        _lib.check(L.daisy_formfactors_set_peers(optixP._ctx, blob, world), "formfactors_set_peers")
+    _lib.check(L.daisy_formfactors_build(optixP._ctx, variant), "formfactors_build")
+    if world > 1:
+        torch.cuda.synchronize()
+        tdist.barrier(group=group)  # peers have finished writing into this rank's rows
+
+
 class _DevMem:
     """Exposes a raw device pointer through __cuda_array_interface__ so torch can alias it without a copy."""
 

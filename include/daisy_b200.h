@@ -97,6 +97,13 @@ int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int nrows, uin
 int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *pairs_owned, int64_t *rays, double *lbvh_ms,
                             double *ff_ms);
 
+/* multi-GPU build without redundant tracing: allocate (and zero) this rank's rows, publish a 64-byte CUDA IPC handle,
+ * receive every rank's handle (nranks x 64 bytes, rank order), then daisy_formfactors_build computes each
+ * upper-triangle tile on exactly one rank and stores the tile / its mirror straight into the owning ranks' matrices
+ * over NVLink.  The host must barrier across ranks after the build before anyone reads the matrix. */
+int daisy_formfactors_alloc(daisy_ctx *ctx);
+int daisy_formfactors_ipc_handle(daisy_ctx *ctx, void *handle64);
+int daisy_formfactors_set_peers(daisy_ctx *ctx, const void *handles, int nranks);
 /* diagnostic: pairs of the last build whose shaft candidate list overflowed and were traced by per-ray LBVH walks */
 int64_t daisy_formfactors_pairs_fallback(daisy_ctx *ctx);
 
