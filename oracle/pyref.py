@@ -213,3 +213,29 @@ def calc_point_ff(op, on, dp, dn, surface):
 def calculate_surface3(a, b, c):
     a, b, c = (np.ascontiguousarray(x, np.float32) for x in (a, b, c))
     return np.float32(lib().ref_calculateSurface3(_fp(a), _fp(b), _fp(c)))
+
+
+# ---- the reference's own CUDA kernel (parallellism.cu), compiled unmodified: GPU box only -------------------------
+def cuda_kernel_available(nofma: bool = False) -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libdaisy_ref_cuda_nofma.so" if nofma else "libdaisy_ref_cuda.so"))
+
+
+def cuda_run_calculate_radiosity_matrix(vertices, normals, tri, nofma: bool = False):
+    """parallellism::runCalculateRadiosityMatrix on the current GPU -> (N x N float64 of Tripl.m_value, wall seconds)."""
+    L = C.CDLL(os.path.join(_HERE, "_ref", "libdaisy_ref_cuda_nofma.so" if nofma else "libdaisy_ref_cuda.so"))
+    f = L.ref_cuda_runCalculateRadiosityMatrix
+    f.restype = C.c_double
+    f.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double)]
+    v = np.ascontiguousarray(vertices, np.float32)
+    n = np.ascontiguousarray(normals, np.float32)
+    t = np.ascontiguousarray(tri, np.int32)
+    out = np.zeros((t.shape[0], t.shape[0]), np.float64)
+    import sys
+    sys.stdout.flush()
+    saved, null = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+    os.dup2(null, 1)  # the reference draws a progress bar on stdout
+    try:
+        secs = f(_fp(v), v.shape[0], _fp(n), n.shape[0], _ip(t), t.shape[0], out.ctypes.data_as(C.POINTER(C.c_double)))
+    finally:
+        os.dup2(saved, 1); os.close(saved); os.close(null)
+    return out, float(secs)

@@ -233,3 +233,57 @@ def test_lightning_classes_match_oracle_loop(dz, cornell2048, uv50, coeff_model)
         assert c.shape == (3,) and np.isfinite(c).all()
         lt.close()
     p.close()
+
+
+@pytest.mark.parametrize("name", ["cornellbox_blacklight", "colorballs"])
+def test_fixture_scene_whole_matrix_digests(dz, fixture_scenes, name):
+    """Every entry of the reference scenes' matrices and every visibility mask, against the whole-matrix digests the CPU
+    oracle froze in tests/golden/<scene>_full_golden.npz (mask hash and F bit-xor per row are exact, row sums to 1e-12)."""
+    import os
+    from conftest import GOLDEN
+    from oracle.pyoracle import row_checksums
+    g = np.load(os.path.join(GOLDEN, name + "_full_golden.npz"))
+    sc = fixture_scenes[name]
+    N = sc.numtriangles
+    p = _ctx(dz, sc, g["uv"])
+    rm = p.cudaCalculateRadiosityMatrix()
+    assert p.stats()["pairs_traced"] == int(g["pairs"]) == {"cornellbox_blacklight": 9322918, "colorballs": 7587047}[name]
+    CH = 512
+    for r0 in range(0, N, CH):
+        nr = min(CH, N - r0)
+        F = rm.rows(r0, nr)
+        m = p.visibilityMasks(r0, nr)
+        mh, fs, fx = row_checksums(F, m)
+        assert np.array_equal(mh, g["mask_hash"][r0:r0 + nr]), (name, r0)
+        assert np.array_equal(fx, g["F_xor"][r0:r0 + nr]), (name, r0)
+        assert np.allclose(fs, g["F_sum"][r0:r0 + nr], rtol=1e-12, atol=1e-15), (name, r0)
+    p.close()
+
+
+def test_unoccluded_vs_reference_cuda_kernel(dz, cornell2048, fixture_scenes, uv50):
+    """The reference's own calculateRow kernel (parallellism.cu, compiled unmodified for sm_100a into oracle/_ref).
+    Its only arithmetic we do not restate is `powf(length, 2)`: nvcc 12.9 expands that into libdevice's polynomial powf
+    (a few ulp off the exact square, and toolkit-version dependent), where we compute length*length.  Built with
+    -fmad=false everything else is the same operation sequence, so the two agree to a few ulp (< 1e-6 relative);
+    built with nvcc's default FMA contraction they agree to 1e-5 wherever the value is not rounding noise."""
+    from oracle import pyref
+    if not pyref.cuda_kernel_available(True):
+        pytest.skip("oracle/_ref/libdaisy_ref_cuda*.so not built (needs /root/reference at build time)")
+    for sc in (cornell2048, fixture_scenes["colorballs"]):
+        N = sc.numtriangles
+        p = _ctx(dz, sc, uv50)
+        ours = p.runCalculateRadiosityMatrix(0, N, 0)["m_value"]
+        for nofma in (True, False):
+            ref, secs = pyref.cuda_run_calculate_radiosity_matrix(sc.vertices, sc.normals, sc.tri, nofma=nofma)
+            assert not ((ours > 0) != (ref > 0)).any()  # the set of mutually facing pairs is identical
+            if nofma:
+                # same operation sequence except powf: a few ulp at most, and most entries identical to the last bit
+                nz = ours > 0
+                assert (np.abs(ours - ref)[nz] / ours[nz]).max() < 1e-6, (sc.name, "nofma")
+                assert (ours[nz] == ref[nz]).mean() > 0.9
+            else:
+                # nvcc's FMA contraction reorders roundings inside the dot products; entries that are themselves
+                # cancellation residue (1e-9 and below, against typical 1e-5..1e-2) carry that noise in full, hence
+                # the absolute floor of 1e-10 next to the 1e-5 relative bar
+                assert np.allclose(ours, ref, rtol=1e-5, atol=1e-10), (sc.name, np.abs(ours - ref).max())
+        p.close()
