@@ -77,13 +77,16 @@ __device__ __forceinline__ WRay wray_setup(f3 o, f3 d) {
     return w;
 }
 
-// returns true on a hit with finite t > 0; u,v = barycentric weights of vertices 1 and 2 (HIT_T_TRIID_U_V)
-__device__ __forceinline__ bool wray_tri(const WRay &w, f3 va, f3 vb, f3 vc, float &t, float &u, float &v) {
+// core of the test with the axis permutation resolved at compile time (no per-component selects)
+template <int KX, int KY, int KZ>
+__device__ __forceinline__ bool wray_tri_k(const WRay &w, f3 va, f3 vb, f3 vc, float &t, float &u, float &v) {
     f3 A = e_sub(va, w.o), B = e_sub(vb, w.o), C = e_sub(vc, w.o);
-    float Akz = comp(A, w.kz), Bkz = comp(B, w.kz), Ckz = comp(C, w.kz);
-    float Ax = fs(comp(A, w.kx), fm(w.Sx, Akz)), Ay = fs(comp(A, w.ky), fm(w.Sy, Akz));
-    float Bx = fs(comp(B, w.kx), fm(w.Sx, Bkz)), By = fs(comp(B, w.ky), fm(w.Sy, Bkz));
-    float Cx = fs(comp(C, w.kx), fm(w.Sx, Ckz)), Cy = fs(comp(C, w.ky), fm(w.Sy, Ckz));
+    const float Akx = KX == 0 ? A.x : (KX == 1 ? A.y : A.z), Aky = KY == 0 ? A.x : (KY == 1 ? A.y : A.z), Akz = KZ == 0 ? A.x : (KZ == 1 ? A.y : A.z);
+    const float Bkx = KX == 0 ? B.x : (KX == 1 ? B.y : B.z), Bky = KY == 0 ? B.x : (KY == 1 ? B.y : B.z), Bkz = KZ == 0 ? B.x : (KZ == 1 ? B.y : B.z);
+    const float Ckx = KX == 0 ? C.x : (KX == 1 ? C.y : C.z), Cky = KY == 0 ? C.x : (KY == 1 ? C.y : C.z), Ckz = KZ == 0 ? C.x : (KZ == 1 ? C.y : C.z);
+    float Ax = fs(Akx, fm(w.Sx, Akz)), Ay = fs(Aky, fm(w.Sy, Akz));
+    float Bx = fs(Bkx, fm(w.Sx, Bkz)), By = fs(Bky, fm(w.Sy, Bkz));
+    float Cx = fs(Ckx, fm(w.Sx, Ckz)), Cy = fs(Cky, fm(w.Sy, Ckz));
     float U = fs(fm(Cx, By), fm(Cy, Bx));
     float V = fs(fm(Ax, Cy), fm(Ay, Cx));
     float W = fs(fm(Bx, Ay), fm(By, Ax));
@@ -101,6 +104,20 @@ __device__ __forceinline__ bool wray_tri(const WRay &w, f3 va, f3 vb, f3 vc, flo
     if (!(tt > 0.0f) || isinf(tt)) return false;
     t = tt; u = fd(V, det); v = fd(W, det);
     return true;
+}
+
+// returns true on a hit with finite t > 0; u,v = barycentric weights of vertices 1 and 2 (HIT_T_TRIID_U_V).
+// (kx,ky,kz) is one of six permutations; rays of one patch pair are nearly parallel, so the switch is almost always
+// uniform across a warp.
+__device__ __forceinline__ bool wray_tri(const WRay &w, f3 va, f3 vb, f3 vc, float &t, float &u, float &v) {
+    switch (w.kz * 2 + (w.kx == (w.kz == 2 ? 0 : w.kz + 1) ? 0 : 1)) {
+    case 0: return wray_tri_k<1, 2, 0>(w, va, vb, vc, t, u, v);
+    case 1: return wray_tri_k<2, 1, 0>(w, va, vb, vc, t, u, v);
+    case 2: return wray_tri_k<2, 0, 1>(w, va, vb, vc, t, u, v);
+    case 3: return wray_tri_k<0, 2, 1>(w, va, vb, vc, t, u, v);
+    case 4: return wray_tri_k<0, 1, 2>(w, va, vb, vc, t, u, v);
+    default: return wray_tri_k<1, 0, 2>(w, va, vb, vc, t, u, v);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -122,6 +139,17 @@ __device__ __forceinline__ bool ray_box(f3 o, f3 inv, float lox, float loy, floa
     float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
     float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
     tnear = tn;
+    return tn <= tf * 1.00001f + 1e-30f;
+}
+
+// same test with the origin pre-multiplied: t = box*inv - o*inv is one FMA per plane.  inf*0 and inf-inf give NaN, which
+// fminf/fmaxf drop, i.e. the plane is ignored: the test can only become more permissive, never cull a real hit.
+__device__ __forceinline__ bool ray_box_fma(f3 oi, f3 inv, float lox, float loy, float loz, float hix, float hiy, float hiz, float tmax) {
+    float t0x = fmaf(lox, inv.x, -oi.x), t1x = fmaf(hix, inv.x, -oi.x);
+    float t0y = fmaf(loy, inv.y, -oi.y), t1y = fmaf(hiy, inv.y, -oi.y);
+    float t0z = fmaf(loz, inv.z, -oi.z), t1z = fmaf(hiz, inv.z, -oi.z);
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
     return tn <= tf * 1.00001f + 1e-30f;
 }
 

@@ -302,7 +302,11 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         float thi = 0.f, uu, vv, tk;
         bool alive = (i < S) && wray_tri(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv);
         if (alive && wray_tri(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) alive = false;
-        f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+        // reciprocal direction, kept finite: with inv = inf the pre-multiplied form would turn a box that straddles 0 on an
+        // axis the ray is parallel to into (-inf, NaN) and reject it
+        f3 inv = mk3(1.0f / (fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x)), 1.0f / (fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y)),
+                     1.0f / (fabsf(dir.z) > 1e-30f ? dir.z : copysignf(1e-30f, dir.z)));
+        f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
         // Slab tests run in lock step over the list (uniform box loads); a lane that passes one only QUEUES the
         // triangle.  The expensive watertight tests are then issued for whole queues at a time, so a warp instruction
         // slot is spent on them only when many lanes have one pending, not whenever a single lane does.
@@ -332,9 +336,8 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                     kn = __shfl_sync(0xffffffffu, kk, j + 1);
                     b0n = tribox[2 * (size_t)kn]; b1n = tribox[2 * (size_t)kn + 1];
                 }
-                float tn;
-                if (alive && ray_box(o, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi, tn)) { wq[qlen * 32 + lane] = k; qlen++; }
-                if (__any_sync(0xffffffffu, qlen == FF_QCAP)) {
+                if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { wq[qlen * 32 + lane] = k; qlen++; }
+                if (((c0 + j + 1) & (FF_QCAP - 1)) == 0) { // at most FF_QCAP entries can be pending here
                     flush();
                     any_alive = __any_sync(0xffffffffu, alive);
                     if (!any_alive) break;
