@@ -287,7 +287,7 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
 // is accepted with (t_k, k) < (t_hi, hi); lo takes part like any other triangle.
 __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox,
                                                    const TriVerts &Tlo, const TriVerts &Thi, int hi, const int *cand,
-                                                   int ncand, const float *s_uv, int S, int lane, int *wq) {
+                                                   int ncand, const float *s_uv, int S, int lane, int *wq, int *wk, float4 *wb) {
     uint64_t mask = 0;
     for (int pass = 0; pass * 32 < S; pass++) {
         const int i = pass * 32 + lane;
@@ -324,27 +324,31 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         };
         bool any_alive = __any_sync(0xffffffffu, alive);
         for (int c0 = 0; c0 < ncand && any_alive; c0 += 32) {
-            // the list was written by another lane of this warp: read it through L2 (ld.global.cg), 32 ids at a time
-            const int kk = (c0 + lane < ncand) ? __ldcg(cand + c0 + lane) : 0;
+            // stage 32 candidates (id + padded box) in the warp's shared-memory slot: the list was written by another lane
+            // of this warp, so it is read through L2 (ld.global.cg); the boxes are then broadcast LDS.128 in the loop
             const int nb = min(32, ncand - c0);
-            int kn = __shfl_sync(0xffffffffu, kk, 0);
-            float4 b0n = tribox[2 * (size_t)kn], b1n = tribox[2 * (size_t)kn + 1];
-            for (int j = 0; j < nb; j++) {
-                const int k = kn;
-                const float4 b0 = b0n, b1 = b1n;
-                if (j + 1 < nb) { // fetch the next box while this one is tested
-                    kn = __shfl_sync(0xffffffffu, kk, j + 1);
-                    b0n = tribox[2 * (size_t)kn]; b1n = tribox[2 * (size_t)kn + 1];
+            __syncwarp();
+            if (lane < nb) {
+                const int k = __ldcg(cand + c0 + lane);
+                wk[lane] = k;
+                wb[2 * lane] = tribox[2 * (size_t)k];
+                wb[2 * lane + 1] = tribox[2 * (size_t)k + 1];
+            }
+            __syncwarp();
+            for (int j0 = 0; j0 < nb; j0 += FF_QCAP) {
+#pragma unroll
+                for (int jj = 0; jj < FF_QCAP; jj++) {
+                    const int j = j0 + jj;
+                    if (j < nb) {
+                        const float4 b0 = wb[2 * j], b1 = wb[2 * j + 1];
+                        if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { wq[qlen * 32 + lane] = wk[j]; qlen++; }
+                    }
                 }
-                if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { wq[qlen * 32 + lane] = k; qlen++; }
-                if (((c0 + j + 1) & (FF_QCAP - 1)) == 0) { // at most FF_QCAP entries can be pending here
-                    flush();
-                    any_alive = __any_sync(0xffffffffu, alive);
-                    if (!any_alive) break;
-                }
+                flush(); // at most FF_QCAP entries were queued since the last flush
+                any_alive = __any_sync(0xffffffffu, alive);
+                if (!any_alive) break;
             }
         }
-        if (any_alive) flush();
         mask |= (uint64_t)__ballot_sync(0xffffffffu, alive) << (32 * pass);
     }
     return mask;
@@ -384,6 +388,8 @@ struct FFSmem {
     int nlist, next, job, nown, nheavy, hnext;
     float uv[2 * DAISY_MAX_SAMPLES];
     int wq[FF_THREADS / 32][FF_QCAP * 32];
+    int wk[FF_THREADS / 32][32];
+    float4 wb[FF_THREADS / 32][64];
 };
 
 template <int VARIANT>
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
                 const int idj = __shfl_sync(0xffffffffu, idx, j);
                 const int rl = idj >> 6, cl = idj & 63;
                 const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
-                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc, sm.uv, P.S, lane, sm.wq[tid >> 5]);
+                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc, sm.uv, P.S, lane, sm.wq[tid >> 5], sm.wk[tid >> 5], sm.wb[tid >> 5]);
                 if (lane == 0) finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
             }
             __syncwarp();
