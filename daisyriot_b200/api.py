@@ -433,3 +433,159 @@ class BWLightning(Lightning):
     def get_color_of_patch(self, index):
         v = self.lightningvalues[0, index]
         return np.array([v, v, v], np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Camera ray cast + patch-colour interpolation: the step right after the solve and the only other optixQuery
+# consumer (reference OptixPrimeFunctionality::traceScreen, .cpp:83-131; Camera.h:54-80; Drawer::interpolate,
+# Drawer.cpp:161-186).  Rays are generated on the host as in the reference, traced by the closest-hit kernel.
+class Camera:
+    """``Camera`` of ``visual studio/Camera.h``: eye (0,0,10) looking at the origin, 45 (radian, as glm 0.9.8 reads
+    it) field of view, viewport = window size; ``gen_rays_for_screen`` un-projects the near- and far-plane point of
+    every (sub)pixel -- the far-plane POINT is what the reference passes as the ray direction."""
+
+    def __init__(self, width: int, height: int, supersampling: int = 4):
+        self.eye = np.array([0.0, 0.0, 10.0], np.float32)
+        self.dir = np.zeros(3, np.float32)
+        self.up = np.array([0.0, 1.0, 0.0], np.float32)
+        self.pixwidth, self.pixheight, self.supersampling = width, height, supersampling
+        self.viewport = np.array([0.0, 0.0, float(width), float(height)], np.float32)
+        dim = int(math.sqrt(supersampling))
+        step = np.float32(1.0 / (dim + 1))
+        self.antialias_matrix = np.zeros(supersampling * 2, np.float32)  # Camera.h:87-100
+        k = 0
+        for x in range(1, dim + 1):
+            for y in range(1, dim + 1):
+                self.antialias_matrix[k], self.antialias_matrix[k + 1] = np.float32(x) * step, np.float32(y) * step
+                k += 2
+
+    def matrices(self):
+        f32 = np.float32
+        def nrm(v):  # glm::normalize = v * (1 / sqrt(dot)), dot = (x*x + y*y) + z*z
+            t = (v * v).astype(f32)
+            return (v * (f32(1) / np.sqrt(f32(f32(t[0] + t[1]) + t[2]), dtype=f32))).astype(f32)
+        def crs(x, y):  # glm::cross
+            return np.array([f32(x[1] * y[2]) - f32(y[1] * x[2]), f32(x[2] * y[0]) - f32(y[2] * x[0]), f32(x[0] * y[1]) - f32(y[0] * x[1])], f32)
+        def dt(a, b):
+            t = (a * b).astype(f32)
+            return f32(f32(t[0] + t[1]) + t[2])
+        f = nrm((self.dir - self.eye).astype(f32))                                          # glm::lookAt (RH)
+        s = nrm(crs(f, self.up))
+        u = crs(s, f)
+        look = np.eye(4, dtype=f32)  # indexed [col][row] like glm
+        look[0, 0], look[1, 0], look[2, 0] = s
+        look[0, 1], look[1, 1], look[2, 1] = u
+        look[0, 2], look[1, 2], look[2, 2] = -f
+        look[3, 0], look[3, 1], look[3, 2] = -dt(s, self.eye), -dt(u, self.eye), dt(f, self.eye)
+        aspect = f32(self.pixwidth) / f32(self.pixheight)
+        t = f32(math.tan(f32(45.0) / f32(2.0)))                                              # glm::perspective (RH, -1..1)
+        zn, zf = f32(0.1), f32(1000.0)
+        proj = np.zeros((4, 4), f32)
+        proj[0, 0] = f32(1) / (aspect * t)
+        proj[1, 1] = f32(1) / t
+        proj[2, 3] = -1
+        proj[2, 2] = -(zf + zn) / (zf - zn)
+        proj[3, 2] = -(f32(2) * zf * zn) / (zf - zn)
+        return look, proj
+
+    @staticmethod
+    def _mat_mul(a, b):
+        """glm mat4 * mat4 ([col][row] storage, float32, glm's association order)."""
+        r = np.zeros((4, 4), np.float32)
+        for c in range(4):
+            r[c] = ((a[0] * b[c, 0] + a[1] * b[c, 1]) + a[2] * b[c, 2]) + a[3] * b[c, 3]
+        return r
+
+    @staticmethod
+    def _mat_inverse(m):
+        """glm::inverse(mat4) restated in float32 (glm/detail/func_matrix.inl:297-358)."""
+        f = np.float32
+        def co(a, b, c, d):
+            return f(f(m[a[0], a[1]] * m[b[0], b[1]]) - f(m[c[0], c[1]] * m[d[0], d[1]]))
+        C00 = co((2, 2), (3, 3), (3, 2), (2, 3)); C02 = co((1, 2), (3, 3), (3, 2), (1, 3)); C03 = co((1, 2), (2, 3), (2, 2), (1, 3))
+        C04 = co((2, 1), (3, 3), (3, 1), (2, 3)); C06 = co((1, 1), (3, 3), (3, 1), (1, 3)); C07 = co((1, 1), (2, 3), (2, 1), (1, 3))
+        C08 = co((2, 1), (3, 2), (3, 1), (2, 2)); C10 = co((1, 1), (3, 2), (3, 1), (1, 2)); C11 = co((1, 1), (2, 2), (2, 1), (1, 2))
+        C12 = co((2, 0), (3, 3), (3, 0), (2, 3)); C14 = co((1, 0), (3, 3), (3, 0), (1, 3)); C15 = co((1, 0), (2, 3), (2, 0), (1, 3))
+        C16 = co((2, 0), (3, 2), (3, 0), (2, 2)); C18 = co((1, 0), (3, 2), (3, 0), (1, 2)); C19 = co((1, 0), (2, 2), (2, 0), (1, 2))
+        C20 = co((2, 0), (3, 1), (3, 0), (2, 1)); C22 = co((1, 0), (3, 1), (3, 0), (1, 1)); C23 = co((1, 0), (2, 1), (2, 0), (1, 1))
+        v4 = lambda *x: np.array(x, np.float32)
+        F0, F1, F2 = v4(C00, C00, C02, C03), v4(C04, C04, C06, C07), v4(C08, C08, C10, C11)
+        F3, F4, F5 = v4(C12, C12, C14, C15), v4(C16, C16, C18, C19), v4(C20, C20, C22, C23)
+        V0, V1 = v4(m[1, 0], m[0, 0], m[0, 0], m[0, 0]), v4(m[1, 1], m[0, 1], m[0, 1], m[0, 1])
+        V2, V3 = v4(m[1, 2], m[0, 2], m[0, 2], m[0, 2]), v4(m[1, 3], m[0, 3], m[0, 3], m[0, 3])
+        I0 = (V1 * F0 - V2 * F1) + V3 * F2
+        I1 = (V0 * F0 - V2 * F3) + V3 * F4
+        I2 = (V0 * F1 - V1 * F3) + V3 * F5
+        I3 = (V0 * F2 - V1 * F4) + V2 * F5
+        SA, SB = v4(1, -1, 1, -1), v4(-1, 1, -1, 1)
+        inv = np.stack([I0 * SA, I1 * SB, I2 * SA, I3 * SB]).astype(np.float32)
+        row0 = v4(inv[0, 0], inv[1, 0], inv[2, 0], inv[3, 0])
+        d0 = m[0] * row0
+        det = f(f(d0[0] + d0[1]) + f(d0[2] + d0[3]))
+        return (inv * f(f(1) / det)).astype(np.float32)
+
+    def gen_rays_for_screen(self, antialiasing: bool) -> np.ndarray:
+        """(H*W*samples, 6) float32 in the reference's order ``((y*W + x)*samples + sample)`` (Camera.h:54-80); float32
+        arithmetic in glm's operation order (lookAt, perspective, unProject = inverse(proj*model) * clip, / w)."""
+        samples = self.supersampling if antialiasing else 1
+        matrix = self.antialias_matrix if antialiasing else np.zeros(2, np.float32)
+        look, proj = self.matrices()
+        inv = self._mat_inverse(self._mat_mul(proj, look))
+        W, H = self.pixwidth, self.pixheight
+        ys, xs, ss = np.meshgrid(np.arange(H), np.arange(W), np.arange(samples), indexing="ij")
+        x_ = (xs.astype(np.float32) + matrix[2 * ss]).astype(np.float32)
+        y_ = (ys.astype(np.float32) + matrix[2 * ss + 1]).astype(np.float32)
+        out = np.empty((H, W, samples, 6), np.float32)
+        two, one = np.float32(2), np.float32(1)
+        for depth, sl in ((0.0, slice(0, 3)), (1.0, slice(3, 6))):
+            tx = ((x_ - self.viewport[0]) / self.viewport[2]) * two - one
+            ty = ((y_ - self.viewport[1]) / self.viewport[3]) * two - one
+            tz = np.float32(depth) * two - one
+            tw = np.float32(1) * two - one
+            obj = ((inv[0][None, :] * tx[..., None] + inv[1][None, :] * ty[..., None]) + (inv[2] * tz + inv[3] * tw)[None, :]).astype(np.float32)
+            out[..., sl] = obj[..., :3] / obj[..., 3:4]
+        return out.reshape(-1, 6)
+
+
+def triangles_per_vertex(mesh: MeshS):
+    """``MeshS::trianglesPerVertex`` (MeshS.cpp:107-109) as CSR (offsets, triangle ids)."""
+    v = mesh.triangleIndices[:, :3].reshape(-1)
+    t = np.repeat(np.arange(mesh.numtriangles, dtype=np.int64), 3)
+    order = np.argsort(v, kind="stable")
+    counts = np.bincount(v, minlength=mesh.vertices.shape[0])
+    return np.concatenate([[0], np.cumsum(counts)]), t[order]
+
+
+def traceScreen(optixP: OptixPrimeFunctionality, camera: Camera, patch_colors: np.ndarray, radiosityRendering: bool = True,
+                antialiasing: bool = True, material_colors: np.ndarray | None = None, rays: np.ndarray | None = None) -> np.ndarray:
+    """``OptixPrimeFunctionality::traceScreen`` (.cpp:83-131): returns ``optixView`` as (H, W, 3) float32.
+    ``patch_colors`` = ``lightning.get_color_of_patch`` for every patch (N,3)."""
+    mesh = optixP.mesh
+    samples = camera.supersampling if antialiasing else 1
+    rays = camera.gen_rays_for_screen(antialiasing) if rays is None else np.ascontiguousarray(rays, np.float32)
+    hits = optixP.optixQuery(rays.shape[0], rays)
+    tid = hits["triangleId"]
+    hit = hits["t"] > 0
+    T = mesh.triangleIndices
+    safe = np.where(hit, tid, 0)
+    # triangle_math::isFacingBack(eye, triangleId): dot(normalize(centre - eye), avgNormal) >= 0      triangle_math.cpp:76-86
+    a, b, c = (mesh.vertices[T[safe, k]] for k in range(3))
+    centre = ((a + b + c) / np.float32(3)).astype(np.float32)
+    n = (mesh.normals[T[safe, 3]] + mesh.normals[T[safe, 4]] + mesh.normals[T[safe, 5]]) / np.float32(3)
+    n = n / np.linalg.norm(n, axis=1, keepdims=True)
+    d = centre - camera.eye[None, :]
+    d = d / np.linalg.norm(d, axis=1, keepdims=True)
+    front = hit & ~((d * n).sum(1) >= 0)
+    if radiosityRendering:
+        # Drawer::interpolate: colours averaged per vertex over trianglesPerVertex, weighted u*a + v*b + (1-u-v)*c
+        off, tris = triangles_per_vertex(mesh)
+        csum = np.concatenate([np.zeros((1, 3), np.float64), np.cumsum(patch_colors[tris].astype(np.float64), axis=0)])
+        cnt = np.maximum(off[1:] - off[:-1], 1)[:, None]
+        vcol = ((csum[off[1:]] - csum[off[:-1]]) / cnt).astype(np.float32)
+        u, v = hits["u"][:, None], hits["v"][:, None]
+        col = u * vcol[T[safe, 0]] + v * vcol[T[safe, 1]] + (np.float32(1) - u - v) * vcol[T[safe, 2]]
+    else:
+        col = material_colors[mesh.materialIndexPerTriangle[safe]]
+    col = np.where(front[:, None], col, np.float32(0)).astype(np.float32)
+    img = col.reshape(camera.pixheight, camera.pixwidth, samples, 3).sum(2) / np.float32(samples)
+    return np.clip(img, 0.0, 1.0).astype(np.float32)

@@ -215,6 +215,18 @@ def calculate_surface3(a, b, c):
     return np.float32(lib().ref_calculateSurface3(_fp(a), _fp(b), _fp(c)))
 
 
+def camera_rays(width, height, supersampling, antialiasing):
+    """Camera::gen_rays_for_screen of the reference's Camera.h -> (W*H*samples, 6) float32."""
+    L = lib()
+    samples = supersampling if antialiasing else 1
+    out = np.empty((width * height * samples, 6), np.float32)
+    L.ref_camera_rays.restype = C.c_int
+    L.ref_camera_rays.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    n = L.ref_camera_rays(width, height, supersampling, int(antialiasing), _fp(out))
+    assert n == out.shape[0]
+    return out
+
+
 # ---- the reference's own CUDA kernel (parallellism.cu), compiled unmodified: GPU box only -------------------------
 def cuda_kernel_available(nofma: bool = False) -> bool:
     return os.path.exists(os.path.join(_HERE, "_ref", "libdaisy_ref_cuda_nofma.so" if nofma else "libdaisy_ref_cuda.so"))

@@ -39,6 +39,15 @@ public:
 #undef private
 #undef protected
 
+// Camera.h (ray generation of traceScreen) needs the two float3 converters of optix_functionality.cpp:78-84; that file
+// itself cannot be compiled (full OptiX API), so the two one-liners are restated here.
+#include <glm/gtc/matrix_transform.hpp>
+namespace optix_functionality {
+inline optix::float3 glm2optixf3(glm::vec3 v) { return optix::make_float3(v.x, v.y, v.z); }
+inline glm::vec3 optix2glmf3(optix::float3 v) { return glm::vec3(v.x, v.y, v.z); }
+}
+#include "Camera.h"
+
 struct RefScene {
     std::vector<float> wavelengths; // Material keeps a reference to this vector
     MeshS mesh;
@@ -165,6 +174,15 @@ void ref_pair_ray(void *h, int row, int col, float u, float v, float *ray6) {
     optix::float3 o = origin + optix::normalize(dest - origin) * 0.000001f;
     optix::float3 d = optix::normalize(dest - origin);
     ray6[0] = o.x; ray6[1] = o.y; ray6[2] = o.z; ray6[3] = d.x; ray6[4] = d.y; ray6[5] = d.z;
+}
+
+// Camera::gen_rays_for_screen (Camera.h:54-80): out = W*H*samples rays of 6 floats
+int ref_camera_rays(int width, int height, int supersampling, int antialiasing, float *out) {
+    Camera cam(width, height, supersampling);
+    std::vector<optix::float3> rays;
+    cam.gen_rays_for_screen(rays, antialiasing != 0);
+    memcpy(out, rays.data(), rays.size() * sizeof(optix::float3));
+    return (int)(rays.size() / 2);
 }
 
 // ---- Lightning.h -----------------------------------------------------------------------------------

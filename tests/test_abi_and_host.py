@@ -149,3 +149,15 @@ def test_partition_and_exchange_layout():
     assert [dist.padded_K(k) for k in (1, 2, 3, 9, 12, 17, 32)] == [1, 3, 3, 9, 16, 32, 32]
     x = api.cie1931WavelengthToXYZFit(550.0)
     assert x.dtype == np.float32 and abs(x[1] - 0.99) < 0.02
+
+
+def test_camera_rays_match_reference_camera_h():
+    """Camera::gen_rays_for_screen restated in float32 (glm lookAt / perspective / inverse / unProject order) against the
+    reference's own Camera.h compiled in oracle/_ref: bit-exact, with and without supersampling."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built")
+    for (w, h, ss, aa) in [(80, 60, 4, True), (80, 60, 4, False), (33, 17, 9, True)]:
+        mine = api.Camera(w, h, ss).gen_rays_for_screen(aa)
+        ref = pyref.camera_rays(w, h, ss, aa)
+        assert mine.shape == ref.shape and np.array_equal(mine.view(np.uint32), ref.view(np.uint32))

@@ -287,3 +287,45 @@ def test_unoccluded_vs_reference_cuda_kernel(dz, cornell2048, fixture_scenes, uv
                 # the absolute floor of 1e-10 next to the 1e-5 relative bar
                 assert np.allclose(ours, ref, rtol=1e-5, atol=1e-10), (sc.name, np.abs(ours - ref).max())
         p.close()
+
+
+def test_trace_screen_matches_literal_restatement(dz, cornell2048, uv50):
+    """traceScreen (camera rays -> closest hit on the GPU -> isFacingBack -> Drawer::interpolate -> clamp) against a literal
+    per-pixel loop over the oracle's closest hits (reference OptixPrimeFunctionality.cpp:83-131, Drawer.cpp:161-186)."""
+    from daisyriot_b200 import api
+    sc = cornell2048
+    mesh = dz.MeshS.from_scene(sc)
+    p = dz.OptixPrimeFunctionality(mesh, rands=uv50)
+    cam = api.Camera(48, 36, 4)
+    cam.eye = np.array([2.75, 2.75, 14.0], np.float32)   # look into the box from its open side
+    cam.dir = np.array([2.75, 2.75, 0.0], np.float32)
+    rng = np.random.RandomState(2)
+    colors = rng.uniform(0, 1.2, (sc.numtriangles, 3)).astype(np.float32)
+    img = api.traceScreen(p, cam, colors, True, True)
+    rays = cam.gen_rays_for_screen(True)
+    hits = _oracle(sc).query_closest(rays)
+    tpv = [[] for _ in range(len(sc.vertices))]
+    for t in range(sc.numtriangles):
+        for k in range(3):
+            tpv[sc.tri[t, k]].append(t)
+    want = np.zeros((36, 48, 3), np.float32)
+    for y in range(36):
+        for x in range(48):
+            col = np.zeros(3, np.float32)
+            for s_ in range(4):
+                h = hits[(y * 48 + x) * 4 + s_]
+                if h["t"] > 0:
+                    tid = h["triangleId"]
+                    a, b, c = (sc.vertices[sc.tri[tid, k]] for k in range(3))
+                    centre = (a + b + c) / np.float32(3)
+                    n = sc.normals[sc.tri[tid, 3:]].sum(0) / np.float32(3)
+                    n = n / np.linalg.norm(n)
+                    d = centre - cam.eye
+                    d = d / np.linalg.norm(d)
+                    if not (np.dot(d, n) >= 0):
+                        va, vb, vc = (np.mean(colors[tpv[sc.tri[tid, k]]], axis=0) for k in range(3))
+                        col += h["u"] * va + h["v"] * vb + (1 - h["u"] - h["v"]) * vc
+            want[y, x] = np.clip(col / np.float32(4), 0, 1)
+    assert (img > 0).mean() > 0.3  # the box fills a good part of the frame
+    assert np.allclose(img, want, rtol=1e-5, atol=2e-6)
+    p.close()
