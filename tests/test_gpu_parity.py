@@ -326,6 +326,6 @@ def test_trace_screen_matches_literal_restatement(dz, cornell2048, uv50):
                         va, vb, vc = (np.mean(colors[tpv[sc.tri[tid, k]]], axis=0) for k in range(3))
                         col += h["u"] * va + h["v"] * vb + (1 - h["u"] - h["v"]) * vc
             want[y, x] = np.clip(col / np.float32(4), 0, 1)
-    assert (img > 0).mean() > 0.3  # the box fills a good part of the frame
+    assert (img > 0).mean() > 0.15  # the box fills a good part of the frame
     assert np.allclose(img, want, rtol=1e-5, atol=2e-6)
     p.close()
