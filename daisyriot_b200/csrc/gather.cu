@@ -41,8 +41,13 @@ struct daisy_solver {
     unsigned int *d_done = nullptr;
     int R = 8, nsplit = 1, grid = 148, colw = 0;
     bool use_tma = true;
+    bool use_mma = false;               // K = 16 / 32: tcgen05 3xTF32 path (gather_mma.cuh)
+    float *d_split = nullptr;           // [Rh; Rl]: 2*Kp x ncolsP, rewritten at the start of every pass
+    int ncolsP = 0;
     alignas(64) CUtensorMap tmF;        // F rows of this rank: 2-D (ldF x nloc), box 128 x tile rows
     alignas(64) CUtensorMap tmRes[2];   // exchange buffers: 3-D (n x Kp x G), box 128 x Kp x 1
+    alignas(64) CUtensorMap tmFmma;     // F rows, box 32 x 128, SWIZZLE_128B
+    alignas(64) CUtensorMap tmSplit;    // d_split, box 32 x 2*Kp, SWIZZLE_128B
     int numpasses = 0;
     double last_ms = 0.0;
     std::vector<double> sums;   // band sums of the current residual
@@ -339,6 +344,8 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     }
 }
 
+#include "gather_mma.cuh"
+
 struct EpiParams {
     const float *partial; int nsplit, nloc, n;
     const float *M; const int *mat;
@@ -429,7 +436,22 @@ static int launch_pass_K(daisy_solver *s) {
     P.res = s->d_res[s->cur]; P.bstride = s->bstride; P.partial = s->d_partial;
     P.nsplit = s->nsplit; P.colw = s->colw; P.nrb = (s->nloc + G_WARPS * s->R - 1) / (G_WARPS * s->R);
     int rc;
-    if (s->use_tma) {
+    if (s->use_mma && (K == 16 || K == 32)) {
+        if constexpr (K == 16 || K == 32) {
+            constexpr size_t smem = mm_smem_bytes<K>();
+            static bool attr_done = false;
+            if (!attr_done) {
+                DZ_CUDA(cudaFuncSetAttribute(k_gather_mma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_done = true;
+            }
+            k_split_residual<K><<<(s->ncolsP + 255) / 256, 256, 0, c->stream>>>(s->d_res[s->cur], s->bstride, s->n, s->G * s->n, s->ncolsP, s->d_split);
+            DZ_CUDA(cudaGetLastError());
+            P.nrb = (s->nloc + MM_ROWS - 1) / MM_ROWS;
+            k_gather_mma<K><<<s->grid, MM_THREADS, smem, c->stream>>>(P, s->tmFmma, s->tmSplit);
+            DZ_CUDA(cudaGetLastError());
+        }
+        rc = DAISY_OK;
+    } else if (s->use_tma) {
         constexpr int NST = tma_nstage<K>();
         size_t smem = (size_t)NST * tma_stage_bytes<K>() + 2 * NST * sizeof(uint64_t);
         static bool attr_done = false;
@@ -510,6 +532,26 @@ static int make_maps(daisy_solver *s) {
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { daisy_set_error("cuTensorMapEncodeTiled(residual) failed: %d", (int)r); return DAISY_E_CUDA; }
     }
+    if (s->use_mma) {
+        {
+            cuuint64_t dims[2] = { (cuuint64_t)c->ldF, (cuuint64_t)(s->nloc > 0 ? s->nloc : 1) };
+            cuuint64_t strides[1] = { (cuuint64_t)c->ldF * 4 };
+            cuuint32_t box[2] = { MM_SUB, MM_ROWS };
+            cuuint32_t es[2] = { 1, 1 };
+            CUresult r = enc(&s->tmFmma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->d_F, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { daisy_set_error("cuTensorMapEncodeTiled(F, swizzled) failed: %d", (int)r); return DAISY_E_CUDA; }
+        }
+        {
+            cuuint64_t dims[2] = { (cuuint64_t)s->ncolsP, (cuuint64_t)(2 * s->Kp) };
+            cuuint64_t strides[1] = { (cuuint64_t)s->ncolsP * 4 };
+            cuuint32_t box[2] = { MM_SUB, (cuuint32_t)(2 * s->Kp) };
+            cuuint32_t es[2] = { 1, 1 };
+            CUresult r = enc(&s->tmSplit, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, s->d_split, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { daisy_set_error("cuTensorMapEncodeTiled(split residual) failed: %d", (int)r); return DAISY_E_CUDA; }
+        }
+    }
     return DAISY_OK;
 }
 
@@ -519,8 +561,11 @@ static void plan(daisy_solver *s) {
     s->grid = sms;
     const char *env = getenv("DAISY_GATHER");
     s->use_tma = !(env && strcmp(env, "ldg") == 0);
+    // wide band counts run on the tensor cores unless DAISY_GATHER=fp32 (or ldg) asks for the CUDA-core kernels
+    s->use_mma = s->use_tma && s->Kp >= 16 && !(env && strcmp(env, "fp32") == 0);
     int Rs[2];
-    if (s->use_tma) { Rs[0] = Rs[1] = (s->Kp == 32 ? 4 : 8); } // rows per block / G_WARPS: 64-row tiles, 32-row for K=32
+    if (s->use_mma) { Rs[0] = Rs[1] = MM_ROWS / G_WARPS; } // 128-row tiles
+    else if (s->use_tma) { Rs[0] = Rs[1] = (s->Kp == 32 ? 4 : 8); } // rows per block / G_WARPS: 64-row tiles, 32-row for K=32
     else if (s->Kp <= 9) { Rs[0] = 8; Rs[1] = 4; } else { Rs[0] = 2; Rs[1] = 4; }
     int ncols = s->G * s->n;
     int maxsplit = (ncols + 4 * G_TC - 1) / (4 * G_TC); // keep at least 2048 columns per item
@@ -549,7 +594,7 @@ static int padded_K(int K) { return K <= 1 ? 1 : K <= 3 ? 3 : K <= 9 ? 9 : K <= 
 static void free_solver(daisy_solver *s) {
     if (!s) return;
     cudaFree(s->d_res[0]); cudaFree(s->d_res[1]); cudaFree(s->d_B); cudaFree(s->d_E); cudaFree(s->d_M); cudaFree(s->d_mat);
-    cudaFree(s->d_partial); cudaFree(s->d_cta_sums); cudaFree(s->d_done);
+    cudaFree(s->d_partial); cudaFree(s->d_cta_sums); cudaFree(s->d_done); cudaFree(s->d_split);
     if (s->e0) cudaEventDestroy(s->e0);
     if (s->e1) cudaEventDestroy(s->e1);
     delete s;
@@ -611,6 +656,10 @@ extern "C" int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const 
     SC(cudaMemset(s->d_res[1], 0, exb));
     SC(cudaEventCreate(&s->e0));
     SC(cudaEventCreate(&s->e1));
+    if (s->use_mma) {
+        s->ncolsP = ((s->G * s->n + 63) / 64) * 64;
+        SC(cudaMalloc(&s->d_split, sizeof(float) * (size_t)2 * s->Kp * s->ncolsP));
+    }
     if (s->use_tma) { int mrc = make_maps(s); if (mrc) { free_solver(s); return mrc; } }
     {
         std::vector<float> ex;
