@@ -29,7 +29,7 @@ static void free_ctx(daisy_ctx *c) {
     if (c->peers_set)
         for (int g = 0; g < c->nranks && g < 16; g++)
             if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
-    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom);
+    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane);
     cudaFree(c->d_nodes); cudaFree(c->d_F);
     delete c;
 }
@@ -79,12 +79,14 @@ extern "C" int daisy_ctx_create(const float *vertices, int nv, const float *norm
         }
     float ext = 0.f;
     for (int d = 0; d < 3; d++) if (ntri) ext = fmaxf(ext, c->scene_hi[d] - c->scene_lo[d]);
+    c->ext = ext;
     c->pad = 1e-4f * ext; // conservative box padding; results never depend on it (tests compare with brute force)
 #define CC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { daisy_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); free_ctx(c); return DAISY_E_CUDA; } } while (0)
     CC(cudaMalloc(&c->d_vertices, sizeof(float) * 3 * (size_t)(nv > 0 ? nv : 1)));
     CC(cudaMalloc(&c->d_normals, sizeof(float) * 3 * (size_t)(nn > 0 ? nn : 1)));
     CC(cudaMalloc(&c->d_tri, sizeof(int) * 6 * (size_t)(ntri > 0 ? ntri : 1)));
     CC(cudaMalloc(&c->d_geom, sizeof(PatchGeom) * (size_t)(ntri > 0 ? ntri : 1)));
+    CC(cudaMalloc(&c->d_plane, sizeof(float4) * (size_t)(ntri > 0 ? ntri : 1)));
     if (nv) CC(cudaMemcpy(c->d_vertices, vertices, sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice));
     if (nn) CC(cudaMemcpy(c->d_normals, normals, sizeof(float) * 3 * (size_t)nn, cudaMemcpyHostToDevice));
     if (ntri) CC(cudaMemcpy(c->d_tri, tri_idx, sizeof(int) * 6 * (size_t)ntri, cudaMemcpyHostToDevice));

@@ -107,8 +107,11 @@ __device__ __forceinline__ bool wray_tri_k(const WRay &w, f3 va, f3 vb, f3 vc, f
 }
 
 // returns true on a hit with finite t > 0; u,v = barycentric weights of vertices 1 and 2 (HIT_T_TRIID_U_V).
-// (kx,ky,kz) is one of six permutations; rays of one patch pair are nearly parallel, so the switch is almost always
-// uniform across a warp.
+// (kx,ky,kz) is one of six permutations.  wray_tri dispatches to a permutation-specialised body (no per-component
+// selects; rays of one patch pair are nearly parallel, so the switch is almost always uniform across a warp) -- six
+// copies of the test, used where code size does not matter.  wray_tri_sel resolves the permutation with selects: one
+// copy, the form the form-factor kernel uses to stay inside the instruction cache.  Both evaluate the identical
+// sequence of IEEE operations on the identical operands, so their results are bit-identical.
 __device__ __forceinline__ bool wray_tri(const WRay &w, f3 va, f3 vb, f3 vc, float &t, float &u, float &v) {
     switch (w.kz * 2 + (w.kx == (w.kz == 2 ? 0 : w.kz + 1) ? 0 : 1)) {
     case 0: return wray_tri_k<1, 2, 0>(w, va, vb, vc, t, u, v);
@@ -118,6 +121,33 @@ __device__ __forceinline__ bool wray_tri(const WRay &w, f3 va, f3 vb, f3 vc, flo
     case 4: return wray_tri_k<0, 1, 2>(w, va, vb, vc, t, u, v);
     default: return wray_tri_k<1, 0, 2>(w, va, vb, vc, t, u, v);
     }
+}
+
+__device__ __forceinline__ bool wray_tri_sel(const WRay &w, f3 va, f3 vb, f3 vc, float &t, float &u, float &v) {
+    f3 A = e_sub(va, w.o), B = e_sub(vb, w.o), C = e_sub(vc, w.o);
+    const float Akx = comp(A, w.kx), Aky = comp(A, w.ky), Akz = comp(A, w.kz);
+    const float Bkx = comp(B, w.kx), Bky = comp(B, w.ky), Bkz = comp(B, w.kz);
+    const float Ckx = comp(C, w.kx), Cky = comp(C, w.ky), Ckz = comp(C, w.kz);
+    float Ax = fs(Akx, fm(w.Sx, Akz)), Ay = fs(Aky, fm(w.Sy, Akz));
+    float Bx = fs(Bkx, fm(w.Sx, Bkz)), By = fs(Bky, fm(w.Sy, Bkz));
+    float Cx = fs(Ckx, fm(w.Sx, Ckz)), Cy = fs(Cky, fm(w.Sy, Ckz));
+    float U = fs(fm(Cx, By), fm(Cy, Bx));
+    float V = fs(fm(Ax, Cy), fm(Ay, Cx));
+    float W = fs(fm(Bx, Ay), fm(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = __double2float_rn(__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx)));
+        V = __double2float_rn(__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx)));
+        W = __double2float_rn(__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax)));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    float det = fa(fa(U, V), W);
+    if (det == 0.0f) return false;
+    float Az = fm(w.Sz, Akz), Bz = fm(w.Sz, Bkz), Cz = fm(w.Sz, Ckz);
+    float T = fa(fa(fm(U, Az), fm(V, Bz)), fm(W, Cz));
+    float tt = fd(T, det);
+    if (!(tt > 0.0f) || isinf(tt)) return false;
+    t = tt; u = fd(V, det); v = fd(W, det);
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -168,12 +198,15 @@ struct daisy_ctx {
     int rank = 0, nranks = 1, rows_per_rank = 0, row0 = 0, row1 = 0;
     int S = 0;
     float h_uv[2 * DAISY_MAX_SAMPLES];
+    int n_nonedge = 0;     // samples [0, n_nonedge) of the device-side (permuted) pattern lie well inside the triangle
     // device mesh
     float *d_vertices = nullptr, *d_normals = nullptr;
     int *d_tri = nullptr;
     TriVerts *d_triverts = nullptr;
     float4 *d_tribox = nullptr; // padded per-triangle boxes (2 float4 each), same boxes as the LBVH leaves
     PatchGeom *d_geom = nullptr;
+    float4 *d_plane = nullptr;  // per triangle: unit geometric normal, w = smallest altitude if coplanar skipping is safe for it, else -1
+    float ext = 0.f;            // largest scene extent
     // LBVH
     BvhNode *d_nodes = nullptr;
     int root = 0;

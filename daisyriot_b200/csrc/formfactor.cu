@@ -10,16 +10,35 @@
 // rays in registers, walks the LBVH, and writes both mirrored tiles coalesced through shared memory.
 #include "daisy_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 #define TILE 64
 #define FF_THREADS 256
 #define PI_D 3.14159265358979323846
 #define PI_F 3.14159265358979323846f
 
+// Sample pattern in DEVICE order: samples whose barycentric margin min(u, v, 1-u-v) is at least EDGE_MARGIN come first
+// ("inner" samples), the rest ("edge" samples) last; c_perm maps a device position back to the caller's sample index
+// (= bit position in the visibility mask).  Rays of inner samples leave and reach the two patches well inside them, which
+// is what lets coplanar neighbours be skipped for them (see k_tri_planes / shaft_candidates).
+#define EDGE_MARGIN 0.02f
 __constant__ float c_uv[2 * DAISY_MAX_SAMPLES];
+__constant__ int c_perm[DAISY_MAX_SAMPLES];
 
 int dz_set_samples_const(daisy_ctx *ctx) {
-    DZ_CUDA(cudaMemcpyToSymbolAsync(c_uv, ctx->h_uv, sizeof(float) * 2 * DAISY_MAX_SAMPLES, 0, cudaMemcpyHostToDevice, ctx->stream));
+    float uv[2 * DAISY_MAX_SAMPLES] = { 0 };
+    int perm[DAISY_MAX_SAMPLES] = { 0 };
+    int n = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = 0; i < ctx->S; i++) {
+            const float u = ctx->h_uv[2 * i], v = ctx->h_uv[2 * i + 1];
+            const bool inner = fminf(fminf(u, v), 1.0f - u - v) >= EDGE_MARGIN;
+            if (inner == (pass == 0)) { uv[2 * n] = u; uv[2 * n + 1] = v; perm[n] = i; n++; }
+        }
+        if (pass == 0) ctx->n_nonedge = n;
+    }
+    DZ_CUDA(cudaMemcpyToSymbolAsync(c_uv, uv, sizeof(uv), 0, cudaMemcpyHostToDevice, ctx->stream));
+    DZ_CUDA(cudaMemcpyToSymbolAsync(c_perm, perm, sizeof(perm), 0, cudaMemcpyHostToDevice, ctx->stream));
     DZ_CUDA(cudaStreamSynchronize(ctx->stream));
     return DAISY_OK;
 }
@@ -56,9 +75,110 @@ __global__ void k_patch_geom(const float *__restrict__ vertices, const float *__
     geom[p] = g;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-triangle plane record for coplanar skipping.  A triangle k that lies in the plane of patch t and does not overlap
+// t can never be hit by a ray that starts (or ends) inside t by a margin and leaves (reaches) the plane steeply: the ray
+// meets the plane once, at a point inside t, so the watertight test's edge functions for k have mixed signs by a margin far
+// above rounding.  The shaft walk uses that to drop such k for the inner samples.  This kernel establishes the static
+// part of the premise for every t: it is not degenerate or sliver-shaped, and NO coplanar triangle overlaps it (checked
+// with a 2-D separating-axis test against every triangle whose padded box meets t's box; coplanar neighbours that are
+// slivers or much larger than t also disqualify t, because the rounding bound scales with their size).
+// plane[t] = (unit normal, smallest altitude h_t) or w = -1 if t does not qualify.  Double precision: runs once.
+struct d3 { double x, y, z; };
+__device__ __forceinline__ d3 dsub(d3 a, d3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+__device__ __forceinline__ double ddot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ d3 dcross(d3 a, d3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+__device__ __forceinline__ d3 dv(float4 v) { return { (double)v.x, (double)v.y, (double)v.z }; }
+
+// true if the projections of triangles P and Q onto the plane (origin o, axes ux, uy) overlap by more than tol
+__device__ bool tri_overlap_2d(const d3 *P, const d3 *Q, d3 o, d3 ux, d3 uy, double tol) {
+    double px[6], py[6];
+    for (int i = 0; i < 3; i++) {
+        d3 a = dsub(P[i], o), b = dsub(Q[i], o);
+        px[i] = ddot(a, ux); py[i] = ddot(a, uy);
+        px[3 + i] = ddot(b, ux); py[3 + i] = ddot(b, uy);
+    }
+    for (int t = 0; t < 2; t++)
+        for (int e = 0; e < 3; e++) {
+            const int i0 = 3 * t + e, i1 = 3 * t + (e + 1) % 3;
+            double ax = -(py[i1] - py[i0]), ay = px[i1] - px[i0];
+            const double len = sqrt(ax * ax + ay * ay);
+            if (len <= 0.0) continue;
+            ax /= len; ay /= len;
+            double mnP = 1e300, mxP = -1e300, mnQ = 1e300, mxQ = -1e300;
+            for (int i = 0; i < 3; i++) {
+                const double a = px[i] * ax + py[i] * ay, b = px[3 + i] * ax + py[3 + i] * ay;
+                mnP = fmin(mnP, a); mxP = fmax(mxP, a); mnQ = fmin(mnQ, b); mxQ = fmax(mxQ, b);
+            }
+            if (fmin(mxP, mxQ) - fmax(mnP, mnQ) <= tol) return false; // separated (or only touching) along this axis
+        }
+    return true;
+}
+
+__global__ void k_tri_planes(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox, const BvhNode *__restrict__ nodes, int root,
+                             int N, double tau, double tau2, float4 *__restrict__ plane) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const TriVerts T = tv[t];
+    const d3 P[3] = { dv(T.a), dv(T.b), dv(T.c) };
+    const d3 e1 = dsub(P[1], P[0]), e2 = dsub(P[2], P[0]), e3 = dsub(P[2], P[1]);
+    d3 n = dcross(e1, e2);
+    const double A2 = sqrt(ddot(n, n));
+    if (!(A2 > 0.0)) { plane[t] = make_float4(0.f, 0.f, 0.f, -1.f); return; }
+    n = { n.x / A2, n.y / A2, n.z / A2 };
+    const double maxe = sqrt(fmax(ddot(e1, e1), fmax(ddot(e2, e2), ddot(e3, e3))));
+    const double h = A2 / maxe;
+    bool safe = h * 8.0 >= maxe;
+    const double l1 = sqrt(ddot(e1, e1));
+    const d3 ux = { e1.x / l1, e1.y / l1, e1.z / l1 };
+    const d3 uy = dcross(n, ux);
+    const float4 b0 = tribox[2 * (size_t)t], b1 = tribox[2 * (size_t)t + 1];
+    int stack[64];
+    int sp = 0, cur = root;
+    while (safe) {
+        if (cur < 0) {
+            const int k = ~cur;
+            if (k != t) {
+                const TriVerts K = tv[k];
+                const d3 Q[3] = { dv(K.a), dv(K.b), dv(K.c) };
+                double dist = 0.0;
+                for (int j = 0; j < 3; j++) dist = fmax(dist, fabs(ddot(n, dsub(Q[j], P[0]))));
+                if (dist <= 4.0 * tau) { // coplanar neighbour
+                    const d3 f1 = dsub(Q[1], Q[0]), f2 = dsub(Q[2], Q[0]), f3 = dsub(Q[2], Q[1]);
+                    const d3 nk = dcross(f1, f2);
+                    const double A2k = sqrt(ddot(nk, nk));
+                    const double maxk = sqrt(fmax(ddot(f1, f1), fmax(ddot(f2, f2), ddot(f3, f3))));
+                    if (!(A2k > 0.0) || (A2k / maxk) * 8.0 < maxk || maxk > 16.0 * h) safe = false;
+                    else if (tri_overlap_2d(P, Q, P[0], ux, uy, tau2)) safe = false;
+                }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+            continue;
+        }
+        const BvhNode nd = nodes[cur];
+        const bool hl = !(nd.a.x > b1.x || nd.a.w < b0.x || nd.a.y > b1.y || nd.b.x < b0.y || nd.a.z > b1.z || nd.b.y < b0.z);
+        const bool hr = !(nd.b.z > b1.x || nd.c.y < b0.x || nd.b.w > b1.y || nd.c.z < b0.y || nd.c.x > b1.z || nd.c.w < b0.z);
+        if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
+        else if (hl) cur = nd.d.x;
+        else if (hr) cur = nd.d.y;
+        else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    plane[t] = make_float4((float)n.x, (float)n.y, (float)n.z, safe ? (float)h : -1.f);
+}
+
+#define COPLANAR_TAU 3e-7f // x scene extent: a triangle within this distance of a patch's plane counts as coplanar
+#define OVERLAP_TAU 2e-6f  // x scene extent: projected overlap below this is "touching", not overlapping
 int dz_precompute_geom(daisy_ctx *ctx) {
     if (ctx->N == 0) return DAISY_OK;
     k_patch_geom<<<(ctx->N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_vertices, ctx->d_normals, ctx->d_tri, ctx->N, ctx->d_geom);
+    DZ_CUDA(cudaGetLastError());
+    k_tri_planes<<<(ctx->N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_triverts, ctx->d_tribox, ctx->d_nodes, ctx->root, ctx->N,
+                                                             (double)COPLANAR_TAU * ctx->ext, (double)OVERLAP_TAU * ctx->ext, ctx->d_plane);
     DZ_CUDA(cudaGetLastError());
     return DAISY_OK;
 }
@@ -145,7 +265,7 @@ int dz_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_t
 // occlusion query bounded by the hit on hi itself: the ray sees hi iff the watertight test accepts hi at t_hi and
 // no other triangle k is accepted with (t_k, k) < (t_hi, hi) lexicographically -- the same predicate, but the
 // traversal can stop at the first occluder and never looks beyond t_hi.
-__device__ __forceinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root,
+__device__ __noinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root,
                                          const TriVerts &Tlo, const TriVerts &Thi, int lo, int hi, float u, float v) {
     // uv2xyz: a + u*(b-a) + v*(c-a)                                                   triangle_math.cpp:3-9
     f3 a0 = xyz(Tlo.a), a1 = xyz(Thi.a);
@@ -155,10 +275,10 @@ __device__ __forceinline__ bool ray_sees(const BvhNode *__restrict__ nodes, cons
     f3 o = e_add(org, e_scale(dir, 0.000001f)); // origin + normalize(dest - origin)*0.000001f
     WRay w = wray_setup(o, dir);
     float thi, uu, vv;
-    if (!wray_tri(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv)) return false;
+    if (!wray_tri_sel(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv)) return false;
     float tk;
     // the origin patch itself takes part like any other triangle (lo < hi, so a tie on t hides hi)
-    if (wray_tri(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) return false;
+    if (wray_tri_sel(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) return false;
     f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
     int stack[64];
     int sp = 0;
@@ -168,7 +288,7 @@ __device__ __forceinline__ bool ray_sees(const BvhNode *__restrict__ nodes, cons
             int k = ~cur;
             if (k != lo && k != hi) {
                 TriVerts t = tv[k];
-                if (wray_tri(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return false;
+                if (wray_tri_sel(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return false;
             }
             if (sp == 0) break;
             cur = stack[--sp];
@@ -250,26 +370,55 @@ __device__ __forceinline__ bool shaft_box(const Shaft &s, float lox, float loy, 
     return true;
 }
 
-// collect the triangles (other than lo and hi) whose leaf box meets the shaft; returns -1 if more than SHAFT_CAP
-__device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, int root, const Shaft &sh, int lo, int hi, int *__restrict__ cand) {
-    int n = 0;
+// Premise of coplanar skipping for one side of a pair (see k_tri_planes): unit normal n and a point a of the patch's
+// plane; on = the patch qualifies and every ray of the pair meets the plane steeply enough.
+struct RingSide { float nx, ny, nz, ax, ay, az; bool on; };
+
+// true if all three vertices of T lie within tau of the plane (n, a)
+__device__ __forceinline__ bool tri_in_plane(const RingSide &r, const TriVerts &T, float tau) {
+    const float d0 = r.nx * (T.a.x - r.ax) + r.ny * (T.a.y - r.ay) + r.nz * (T.a.z - r.az);
+    const float d1 = r.nx * (T.b.x - r.ax) + r.ny * (T.b.y - r.ay) + r.nz * (T.b.z - r.az);
+    const float d2 = r.nx * (T.c.x - r.ax) + r.ny * (T.c.y - r.ay) + r.nz * (T.c.z - r.az);
+    return fmaxf(fabsf(d0), fmaxf(fabsf(d1), fabsf(d2))) <= tau;
+}
+// cheap pre-test with the leaf's padded box: can the plane pass through it at all?
+__device__ __forceinline__ bool box_meets_plane(const RingSide &r, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    const float cx = 0.5f * (lox + hix) - r.ax, cy = 0.5f * (loy + hiy) - r.ay, cz = 0.5f * (loz + hiz) - r.az;
+    const float rad = 0.5f * ((hix - lox) * fabsf(r.nx) + (hiy - loy) * fabsf(r.ny) + (hiz - loz) * fabsf(r.nz));
+    return fabsf(r.nx * cx + r.ny * cy + r.nz * cz) <= rad;
+}
+
+// collect the triangles (other than lo and hi) whose leaf box meets the shaft.  Triangles coplanar with lo (or hi) when
+// that side's premise holds go to the RING list, stored downwards from the end of the slot: only the edge samples have to
+// test them.  Everything else goes to the MAIN list at the start of the slot.  Returns n_main | n_ring << 16, or -1 if the
+// two lists do not fit SHAFT_CAP.
+__device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root, const Shaft &sh,
+                                                const RingSide &rl, const RingSide &rh, float tau, int lo, int hi, int *__restrict__ cand) {
+    int n_main = 0, n_ring = 0;
     int stack[64];
     int sp = 0;
     int cur = root;
-    while (true) {
-        if (cur < 0) {
-            int k = ~cur;
-            if (k != lo && k != hi) {
-                if (n == SHAFT_CAP) return -1;
-                cand[n++] = k;
-            }
-            if (sp == 0) break;
-            cur = stack[--sp];
-            continue;
+    bool overflow = false;
+    auto leaf = [&](int k, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+        if (k == lo || k == hi) return;
+        if (n_main + n_ring == SHAFT_CAP) { overflow = true; return; }
+        bool ring = false;
+        const bool tl = rl.on && box_meets_plane(rl, lox, loy, loz, hix, hiy, hiz);
+        const bool th = rh.on && box_meets_plane(rh, lox, loy, loz, hix, hiy, hiz);
+        if (tl || th) {
+            const TriVerts T = tv[k];
+            ring = (tl && tri_in_plane(rl, T, tau)) || (th && tri_in_plane(rh, T, tau));
         }
+        if (ring) cand[SHAFT_CAP - 1 - n_ring++] = k;
+        else cand[n_main++] = k;
+    };
+    if (cur < 0) return 0; // single-triangle hierarchy: no third triangle exists
+    while (!overflow) {
         BvhNode nd = nodes[cur];
         bool hl = shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
         bool hr = shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
+        if (hl && nd.d.x < 0) { leaf(~nd.d.x, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y); hl = false; }
+        if (hr && nd.d.y < 0) { leaf(~nd.d.y, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w); hr = false; }
         if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
         else if (hl) cur = nd.d.x;
         else if (hr) cur = nd.d.y;
@@ -278,17 +427,19 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
             cur = stack[--sp];
         }
     }
-    return n;
+    return overflow ? -1 : (n_main | (n_ring << 16));
 }
 
-// Visibility mask of one pair with the whole warp: lane = sample, the candidate list is walked in lock step (uniform
-// loads), each candidate first meets a cheap conservative slab test against its padded box and only then the
+// Visibility mask of one pair with the whole warp: lane = sample (device order), a candidate list is walked in lock step
+// (uniform loads), each candidate first meets a cheap conservative slab test against its padded box and only then the
 // watertight test.  Same predicate as ray_sees: sample i sees hi iff hi is accepted at t_hi and no other triangle k
-// is accepted with (t_k, k) < (t_hi, hi); lo takes part like any other triangle.
+// is accepted with (t_k, k) < (t_hi, hi); lo takes part like any other triangle.  The main list is tested by every
+// sample, the ring list (coplanar with lo or hi, see shaft_candidates) only by the edge samples.
 __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox,
                                                    const TriVerts &Tlo, const TriVerts &Thi, int hi, const int *cand,
-                                                   int ncand, const float *s_uv, int S, int lane, int *wq, int *wk, float4 *wb) {
-    uint64_t mask = 0;
+                                                   int n_main, int n_ring, int n_inner, float m_req, const float *s_uv, const unsigned char *s_perm, int S,
+                                                   int lane, int *wq, int *wk, float4 *wb) {
+    unsigned mask_lo = 0, mask_hi = 0;
     for (int pass = 0; pass * 32 < S; pass++) {
         const int i = pass * 32 + lane;
         const int ii = min(i, S - 1);
@@ -300,8 +451,8 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         f3 o = e_add(org, e_scale(dir, 0.000001f));
         WRay w = wray_setup(o, dir);
         float thi = 0.f, uu, vv, tk;
-        bool alive = (i < S) && wray_tri(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv);
-        if (alive && wray_tri(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) alive = false;
+        bool alive = (i < S) && wray_tri_sel(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv);
+        if (alive && wray_tri_sel(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) alive = false;
         // reciprocal direction, kept finite: with inv = inf the pre-multiplied form would turn a box that straddles 0 on an
         // axis the ray is parallel to into (-inf, NaN) and reject it
         f3 inv = mk3(1.0f / (fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x)), 1.0f / (fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y)),
@@ -317,41 +468,78 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 if (alive && t < qlen) {
                     const int k = wq[t * 32 + lane];
                     TriVerts tr = tv[k];
-                    if (wray_tri(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) alive = false;
+                    if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) alive = false;
                 }
             }
             qlen = 0;
         };
-        bool any_alive = __any_sync(0xffffffffu, alive);
-        for (int c0 = 0; c0 < ncand && any_alive; c0 += 32) {
-            // stage 32 candidates (id + padded box) in the warp's shared-memory slot: the list was written by another lane
-            // of this warp, so it is read through L2 (ld.global.cg); the boxes are then broadcast LDS.128 in the loop
-            const int nb = min(32, ncand - c0);
-            __syncwarp();
-            if (lane < nb) {
-                const int k = __ldcg(cand + c0 + lane);
-                wk[lane] = k;
-                wb[2 * lane] = tribox[2 * (size_t)k];
-                wb[2 * lane + 1] = tribox[2 * (size_t)k + 1];
-            }
-            __syncwarp();
-            for (int j0 = 0; j0 < nb; j0 += FF_QCAP) {
-#pragma unroll
-                for (int jj = 0; jj < FF_QCAP; jj++) {
-                    const int j = j0 + jj;
-                    if (j < nb) {
-                        const float4 b0 = wb[2 * j], b1 = wb[2 * j + 1];
-                        if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { wq[qlen * 32 + lane] = wk[j]; qlen++; }
-                    }
+        {
+            bool any_alive = __any_sync(0xffffffffu, alive);
+            for (int c0 = 0; c0 < n_main && any_alive; c0 += 32) {
+                // stage 32 candidates (id + padded box) in the warp's shared-memory slot: the list was written by another lane
+                // of this warp, so it is read through L2 (ld.global.cg); the boxes are then broadcast LDS.128 in the loop
+                const int nb = min(32, n_main - c0);
+                __syncwarp();
+                if (lane < nb) {
+                    const int k = __ldcg(cand + c0 + lane);
+                    wk[lane] = k;
+                    wb[2 * lane] = tribox[2 * (size_t)k];
+                    wb[2 * lane + 1] = tribox[2 * (size_t)k + 1];
                 }
-                flush(); // at most FF_QCAP entries were queued since the last flush
-                any_alive = __any_sync(0xffffffffu, alive);
-                if (!any_alive) break;
+                __syncwarp();
+                for (int j0 = 0; j0 < nb; j0 += FF_QCAP) {
+#pragma unroll
+                    for (int jj = 0; jj < FF_QCAP; jj++) {
+                        const int j = j0 + jj;
+                        if (j < nb) {
+                            const float4 b0 = wb[2 * j], b1 = wb[2 * j + 1];
+                            if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { wq[qlen * 32 + lane] = wk[j]; qlen++; }
+                        }
+                    }
+                    flush(); // at most FF_QCAP entries were queued since the last flush
+                    any_alive = __any_sync(0xffffffffu, alive);
+                    if (!any_alive) break;
+                }
             }
         }
-        mask |= (uint64_t)__ballot_sync(0xffffffffu, alive) << (32 * pass);
+        // Ring list (coplanar with lo or hi): only samples closer to an edge of their triangles than the pair's required
+        // margin have to test it.  They are few (usually 1-6 of 50), so the roles flip: the edge sample's ray is broadcast
+        // and lane = ring candidate.
+        if (n_ring > 0 && pass * 32 + 31 >= n_inner) {
+            const float mg = fminf(fminf(u, v), 1.0f - u - v);
+            unsigned edge = __ballot_sync(0xffffffffu, alive && i >= n_inner && mg < m_req);
+            while (edge) {
+                const int e = __ffs(edge) - 1;
+                edge &= edge - 1;
+                WRay we;
+                we.o.x = __shfl_sync(0xffffffffu, w.o.x, e); we.o.y = __shfl_sync(0xffffffffu, w.o.y, e); we.o.z = __shfl_sync(0xffffffffu, w.o.z, e);
+                we.kx = __shfl_sync(0xffffffffu, w.kx, e); we.ky = __shfl_sync(0xffffffffu, w.ky, e); we.kz = __shfl_sync(0xffffffffu, w.kz, e);
+                we.Sx = __shfl_sync(0xffffffffu, w.Sx, e); we.Sy = __shfl_sync(0xffffffffu, w.Sy, e); we.Sz = __shfl_sync(0xffffffffu, w.Sz, e);
+                const f3 inve = mk3(__shfl_sync(0xffffffffu, inv.x, e), __shfl_sync(0xffffffffu, inv.y, e), __shfl_sync(0xffffffffu, inv.z, e));
+                const f3 oie = mk3(__shfl_sync(0xffffffffu, oi.x, e), __shfl_sync(0xffffffffu, oi.y, e), __shfl_sync(0xffffffffu, oi.z, e));
+                const float thie = __shfl_sync(0xffffffffu, thi, e);
+                bool hit = false;
+                for (int c0 = 0; c0 < n_ring; c0 += 32) {
+                    if (c0 + lane < n_ring) {
+                        const int k = __ldcg(cand + SHAFT_CAP - 1 - (c0 + lane));
+                        const float4 b0 = tribox[2 * (size_t)k], b1 = tribox[2 * (size_t)k + 1];
+                        if (ray_box_fma(oie, inve, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thie)) {
+                            const TriVerts tr = tv[k];
+                            float t2, u2, v2;
+                            if (wray_tri_sel(we, xyz(tr.a), xyz(tr.b), xyz(tr.c), t2, u2, v2) && (t2 < thie || (t2 == thie && k < hi))) hit = true;
+                        }
+                    }
+                }
+                if (__any_sync(0xffffffffu, hit) && lane == e) alive = false;
+            }
+        }
+        // bit position = the caller's sample index
+        const int bit = s_perm[ii];
+        const unsigned lo_bit = (alive && bit < 32) ? (1u << bit) : 0u, hi_bit = (alive && bit >= 32) ? (1u << (bit - 32)) : 0u;
+        mask_lo |= __reduce_or_sync(0xffffffffu, lo_bit);
+        mask_hi |= __reduce_or_sync(0xffffffffu, hi_bit);
     }
-    return mask;
+    return (uint64_t)mask_lo | ((uint64_t)mask_hi << 32);
 }
 
 struct FFParams {
@@ -359,6 +547,10 @@ struct FFParams {
     const TriVerts *tv;
     const BvhNode *nodes;
     const float4 *tribox; // padded triangle boxes, 2 float4 per triangle
+    const float4 *plane;  // per-triangle plane record (k_tri_planes)
+    float tau;            // coplanarity tolerance
+    int n_inner;          // samples [0, n_inner) of the device-order pattern are inner samples
+    int ring_on;          // coplanar skipping enabled
     int *scratch;         // gridDim.x * FF_THREADS * SHAFT_CAP candidate slots
     int root, N, S;
     int row0, row1;      // rows this context owns
@@ -381,6 +573,8 @@ struct FFParams {
 struct FFSmem {
     PatchGeom gr[TILE], gc[TILE];
     TriVerts tr[TILE], tc[TILE];
+    float4 pr[TILE], pc[TILE]; // plane records of the row / column patches
+    unsigned char perm[DAISY_MAX_SAMPLES];
     float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
     float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
     unsigned short list[TILE * TILE];
@@ -393,7 +587,7 @@ struct FFSmem {
 };
 
 template <int VARIANT>
-__global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
+__global__ void __launch_bounds__(FF_THREADS, 2) k_ff_tiles(FFParams P) {
     extern __shared__ __align__(16) unsigned char ff_smem_raw[];
     FFSmem &sm = *reinterpret_cast<FFSmem *>(ff_smem_raw);
     PatchGeom *s_gr = sm.gr, *s_gc = sm.gc;
@@ -406,6 +600,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     if (tid < 2 * DAISY_MAX_SAMPLES) sm.uv[tid] = c_uv[tid];
+    if (tid < DAISY_MAX_SAMPLES) sm.perm[tid] = (unsigned char)c_perm[tid];
     int *my_cand = P.scratch + ((size_t)blockIdx.x * FF_THREADS + tid) * SHAFT_CAP;
     int *warp_cand = P.scratch + ((size_t)blockIdx.x * FF_THREADS + (tid & ~31)) * SHAFT_CAP;
 
@@ -431,10 +626,12 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
             ((float4 *)&s_tr[p])[q] = ((const float4 *)&P.tv[gr])[q];
             ((float4 *)&s_tc[p])[q] = ((const float4 *)&P.tv[gc])[q];
         }
+        if (tid < TILE) sm.pr[tid] = P.plane[min(R0 + tid, P.N - 1)];
+        else if (tid < 2 * TILE) sm.pc[tid - TILE] = P.plane[min(C0 + tid - TILE, P.N - 1)];
         __syncthreads();
 
         // ---- phase 1: unoccluded form factors of every pair r < c of the tile; facing pairs go on the list
-        for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
+        _Pragma("unroll 1") for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
             int rl = idx >> 6, cl = idx & 63;
             int r = R0 + rl, c = C0 + cl;
             bool valid = (r < P.N) && (c < P.N) && (r < c) &&
@@ -501,11 +698,41 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
             // (i) lane = pair: shaft walk, candidates into this lane's global scratch slot
             const int q = q0 + lane;
             int idx = 0, ncand = -2;
+            float m_req = 0.f;
             if (q < nlist) {
                 idx = s_list[q];
                 int rl = idx >> 6, cl = idx & 63;
-                Shaft sh = make_shaft(s_tr[rl], s_tc[cl]);
-                ncand = shaft_candidates(P.nodes, P.root, sh, R0 + rl, C0 + cl, my_cand);
+                const TriVerts &A = s_tr[rl], &B = s_tc[cl];
+                Shaft sh = make_shaft(A, B);
+                // premise of coplanar skipping per side: the patch qualifies (plane.w = its smallest altitude h > 0) and every
+                // ray meets its plane steeply.  The ray directions are convex combinations of the three vertex-to-vertex
+                // vectors D_i, so n.D_i of one sign bounds cos(theta) >= min|n.D_i| / max|D_i|.  The edge functions of a
+                // coplanar triangle near a patch are computed from coordinates relative to the ray origin: rounding
+                // ~ 8 eps (distance) (its size), against a true value >= (EDGE_MARGIN h)(its edge) cos(theta).  With sizes and
+                // aspect ratios bounded by k_tri_planes that gives cos >= 0.02 on the origin side (distance ~ size) and
+                // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
+                RingSide rl_, rh_;
+                rl_.on = rh_.on = false;
+                if (P.ring_on) {
+                    const float4 pl = sm.pr[rl], ph = sm.pc[cl];
+                    const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
+                    const float d1x = B.b.x - A.b.x, d1y = B.b.y - A.b.y, d1z = B.b.z - A.b.z;
+                    const float d2x = B.c.x - A.c.x, d2y = B.c.y - A.c.y, d2z = B.c.z - A.c.z;
+                    const float dmax = sqrtf(fmaxf(d0x * d0x + d0y * d0y + d0z * d0z, fmaxf(d1x * d1x + d1y * d1y + d1z * d1z, d2x * d2x + d2y * d2y + d2z * d2z)));
+                    const float l0 = pl.x * d0x + pl.y * d0y + pl.z * d0z, l1 = pl.x * d1x + pl.y * d1y + pl.z * d1z, l2 = pl.x * d2x + pl.y * d2y + pl.z * d2z;
+                    const float h0 = ph.x * d0x + ph.y * d0y + ph.z * d0z, h1 = ph.x * d1x + ph.y * d1y + ph.z * d1z, h2 = ph.x * d2x + ph.y * d2y + ph.z * d2z;
+                    const float lmin = ((l0 > 0.f) == (l1 > 0.f) && (l1 > 0.f) == (l2 > 0.f)) ? fminf(fabsf(l0), fminf(fabsf(l1), fabsf(l2))) : 0.f;
+                    const float hmin = ((h0 > 0.f) == (h1 > 0.f) && (h1 > 0.f) == (h2 > 0.f)) ? fminf(fabsf(h0), fminf(fabsf(h1), fabsf(h2))) : 0.f;
+                    rl_.nx = pl.x; rl_.ny = pl.y; rl_.nz = pl.z; rl_.ax = A.a.x; rl_.ay = A.a.y; rl_.az = A.a.z;
+                    rh_.nx = ph.x; rh_.ny = ph.y; rh_.nz = ph.z; rh_.ax = B.a.x; rh_.ay = B.a.y; rh_.az = B.a.z;
+                    // required margins (fractions of the altitude): m >= 128 eps D / (h cos), D = 32 h on the origin side
+                    const float mlo = (pl.w > 0.f && lmin > 0.f) ? 2.44e-4f * dmax / lmin : 1.f;
+                    const float mhi = (ph.w > 0.f && hmin > 0.f) ? 7.63e-6f * (dmax + 64.f * ph.w) * dmax / (hmin * ph.w) : 1.f;
+                    rl_.on = mlo <= EDGE_MARGIN; // inner samples (margin >= EDGE_MARGIN) are then always safe
+                    rh_.on = mhi <= EDGE_MARGIN;
+                    m_req = fmaxf(rl_.on ? mlo : 0.f, rh_.on ? mhi : 0.f);
+                }
+                ncand = shaft_candidates(P.nodes, P.tv, P.root, sh, rl_, rh_, P.tau, R0 + rl, C0 + cl, my_cand);
                 if (ncand < 0) s_heavy[atomicAdd(&s_nheavy, 1)] = (unsigned short)idx;
             }
             __syncwarp();
@@ -514,9 +741,11 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
                 const int nc = __shfl_sync(0xffffffffu, ncand, j);
                 if (nc < 0) continue;
                 const int idj = __shfl_sync(0xffffffffu, idx, j);
+                const float mrq = __shfl_sync(0xffffffffu, m_req, j);
                 const int rl = idj >> 6, cl = idj & 63;
                 const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
-                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc, sm.uv, P.S, lane, sm.wq[tid >> 5], sm.wk[tid >> 5], sm.wb[tid >> 5]);
+                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, nc >> 16, P.n_inner, mrq,
+                                               sm.uv, sm.perm, P.S, lane, sm.wq[tid >> 5], sm.wk[tid >> 5], sm.wb[tid >> 5]);
                 if (lane == 0) finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
             }
             __syncwarp();
@@ -537,7 +766,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
                 const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
                 uint64_t mask = 0;
                 for (int i = 0; i < P.S; i++)
-                    if (ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, r, c, c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << i);
+                    if (ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, r, c, c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
                 finish_pair(rl, cl, r, c, mask);
             }
         }
@@ -548,7 +777,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
             const int ga = R0 / P.n_per_rank, gb = C0 / P.n_per_rank; // tiles never straddle two ranks (n is a multiple of 128)
             float *Fa = P.Fpeer[ga] - (size_t)ga * P.n_per_rank * P.ldF;
             float *Fb = P.Fpeer[gb] - (size_t)gb * P.n_per_rank * P.ldF;
-            for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
+            _Pragma("unroll 1") for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
                 int a = idx >> 6, b = idx & 63;
                 if (diag) {
                     int r = R0 + a, c = C0 + b;
@@ -561,7 +790,7 @@ __global__ void __launch_bounds__(FF_THREADS) k_ff_tiles(FFParams P) {
                 }
             }
         } else if (P.F) {
-            for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
+            _Pragma("unroll 1") for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
                 int a = idx >> 6, b = idx & 63;
                 if (diag) {
                     int r = R0 + a, c = C0 + b;
@@ -623,6 +852,8 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     DZ_CUDA(cudaMemsetAsync(d_pairs, 0, 3 * sizeof(unsigned long long), st));
     FFParams P;
     P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.tribox = ctx->d_tribox; P.scratch = nullptr; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
+    P.plane = ctx->d_plane; P.tau = COPLANAR_TAU * ctx->ext; P.n_inner = ctx->n_nonedge;
+    { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
     P.peer_mode = peer ? 1 : 0; P.n_per_rank = ctx->rows_per_rank;
