@@ -58,6 +58,7 @@ __device__ __forceinline__ float e_surface(f3 a, f3 b, f3 c) {
 struct WRay {
     f3 o;           // origin
     int kx, ky, kz; // axis permutation, kz = dominant direction axis
+    int perm;       // the same permutation as flags: bit 0 = (kz == 0), bit 1 = (kz == 1), bit 2 = kx and ky swapped (d[kz] < 0)
     float Sx, Sy, Sz;
 };
 __device__ __forceinline__ float comp(const f3 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
@@ -69,6 +70,7 @@ __device__ __forceinline__ WRay wray_setup(f3 o, f3 d) {
     int kz = (ax >= ay && ax >= az) ? 0 : ((ay >= az) ? 1 : 2);
     int kx = kz == 2 ? 0 : kz + 1, ky = kx == 2 ? 0 : kx + 1;
     float dz = comp(d, kz);
+    w.perm = (kz == 0 ? 1 : 0) | (kz == 1 ? 2 : 0) | (dz < 0.0f ? 4 : 0);
     if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }
     w.kx = kx; w.ky = ky; w.kz = kz;
     w.Sx = fd(comp(d, kx), dz);
@@ -125,9 +127,15 @@ __device__ __forceinline__ bool wray_tri(const WRay &w, f3 va, f3 vb, f3 vc, flo
 
 __device__ __forceinline__ bool wray_tri_sel(const WRay &w, f3 va, f3 vb, f3 vc, float &t, float &u, float &v) {
     f3 A = e_sub(va, w.o), B = e_sub(vb, w.o), C = e_sub(vc, w.o);
-    const float Akx = comp(A, w.kx), Aky = comp(A, w.ky), Akz = comp(A, w.kz);
-    const float Bkx = comp(B, w.kx), Bky = comp(B, w.ky), Bkz = comp(B, w.kz);
-    const float Ckx = comp(C, w.kx), Cky = comp(C, w.ky), Ckz = comp(C, w.kz);
+    // (kx, ky, kz) = (kz+1, kz+2, kz) mod 3, kx and ky swapped when the dominant component is negative: a rotation of the
+    // components followed by a conditional swap, 8 selects per vertex on three per-ray flags
+    const bool r0 = w.perm & 1, r1 = w.perm & 2, sw = w.perm & 4;
+    const float A0 = r0 ? A.y : (r1 ? A.z : A.x), A1 = r0 ? A.z : (r1 ? A.x : A.y), Akz = r0 ? A.x : (r1 ? A.y : A.z);
+    const float B0 = r0 ? B.y : (r1 ? B.z : B.x), B1 = r0 ? B.z : (r1 ? B.x : B.y), Bkz = r0 ? B.x : (r1 ? B.y : B.z);
+    const float C0 = r0 ? C.y : (r1 ? C.z : C.x), C1 = r0 ? C.z : (r1 ? C.x : C.y), Ckz = r0 ? C.x : (r1 ? C.y : C.z);
+    const float Akx = sw ? A1 : A0, Aky = sw ? A0 : A1;
+    const float Bkx = sw ? B1 : B0, Bky = sw ? B0 : B1;
+    const float Ckx = sw ? C1 : C0, Cky = sw ? C0 : C1;
     float Ax = fs(Akx, fm(w.Sx, Akz)), Ay = fs(Aky, fm(w.Sy, Akz));
     float Bx = fs(Bkx, fm(w.Sx, Bkz)), By = fs(Bky, fm(w.Sy, Bkz));
     float Cx = fs(Ckx, fm(w.Sx, Ckz)), Cy = fs(Cky, fm(w.Sy, Ckz));

@@ -513,7 +513,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 edge &= edge - 1;
                 WRay we;
                 we.o.x = __shfl_sync(0xffffffffu, w.o.x, e); we.o.y = __shfl_sync(0xffffffffu, w.o.y, e); we.o.z = __shfl_sync(0xffffffffu, w.o.z, e);
-                we.kx = __shfl_sync(0xffffffffu, w.kx, e); we.ky = __shfl_sync(0xffffffffu, w.ky, e); we.kz = __shfl_sync(0xffffffffu, w.kz, e);
+                we.perm = __shfl_sync(0xffffffffu, w.perm, e); we.kx = we.ky = we.kz = 0; // the select-based test reads perm only
                 we.Sx = __shfl_sync(0xffffffffu, w.Sx, e); we.Sy = __shfl_sync(0xffffffffu, w.Sy, e); we.Sz = __shfl_sync(0xffffffffu, w.Sz, e);
                 const f3 inve = mk3(__shfl_sync(0xffffffffu, inv.x, e), __shfl_sync(0xffffffffu, inv.y, e), __shfl_sync(0xffffffffu, inv.z, e));
                 const f3 oie = mk3(__shfl_sync(0xffffffffu, oi.x, e), __shfl_sync(0xffffffffu, oi.y, e), __shfl_sync(0xffffffffu, oi.z, e));
@@ -571,7 +571,17 @@ struct FFParams {
 };
 
 struct FFSmem {
-    PatchGeom gr[TILE], gc[TILE];
+    // phase 1 (sub-patch records of the row / column patches) and phase 2 (per-warp candidate staging) never overlap in
+    // time, so they share storage: at 75 KB per CTA three CTAs fit one SM
+    union {
+        struct { PatchGeom gr[TILE], gc[TILE]; } p1;
+        struct {
+            int wq[FF_THREADS / 32][FF_QCAP * 32];
+            int wk[FF_THREADS / 32][32];
+            float4 wb[FF_THREADS / 32][64];
+        } p2;
+    } u;
+    float area_r[TILE], area_c[TILE]; // patch areas (needed after phase 1 by the host-variant reciprocity rule)
     TriVerts tr[TILE], tc[TILE];
     float4 pr[TILE], pc[TILE]; // plane records of the row / column patches
     unsigned char perm[DAISY_MAX_SAMPLES];
@@ -581,16 +591,13 @@ struct FFSmem {
     unsigned short heavy[TILE * TILE];
     int nlist, next, job, nown, nheavy, hnext;
     float uv[2 * DAISY_MAX_SAMPLES];
-    int wq[FF_THREADS / 32][FF_QCAP * 32];
-    int wk[FF_THREADS / 32][32];
-    float4 wb[FF_THREADS / 32][64];
 };
 
 template <int VARIANT>
-__global__ void __launch_bounds__(FF_THREADS, 2) k_ff_tiles(FFParams P) {
+__global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
     extern __shared__ __align__(16) unsigned char ff_smem_raw[];
     FFSmem &sm = *reinterpret_cast<FFSmem *>(ff_smem_raw);
-    PatchGeom *s_gr = sm.gr, *s_gc = sm.gc;
+    PatchGeom *s_gr = sm.u.p1.gr, *s_gc = sm.u.p1.gc;
     TriVerts *s_tr = sm.tr, *s_tc = sm.tc;
     float(*s_rc)[TILE + 1] = sm.rc;
     float(*s_cr)[TILE + 1] = sm.cr;
@@ -626,8 +633,8 @@ __global__ void __launch_bounds__(FF_THREADS, 2) k_ff_tiles(FFParams P) {
             ((float4 *)&s_tr[p])[q] = ((const float4 *)&P.tv[gr])[q];
             ((float4 *)&s_tc[p])[q] = ((const float4 *)&P.tv[gc])[q];
         }
-        if (tid < TILE) sm.pr[tid] = P.plane[min(R0 + tid, P.N - 1)];
-        else if (tid < 2 * TILE) sm.pc[tid - TILE] = P.plane[min(C0 + tid - TILE, P.N - 1)];
+        if (tid < TILE) { sm.pr[tid] = P.plane[min(R0 + tid, P.N - 1)]; sm.area_r[tid] = P.geom[min(R0 + tid, P.N - 1)].n.w; }
+        else if (tid < 2 * TILE) { sm.pc[tid - TILE] = P.plane[min(C0 + tid - TILE, P.N - 1)]; sm.area_c[tid - TILE] = P.geom[min(C0 + tid - TILE, P.N - 1)].n.w; }
         __syncthreads();
 
         // ---- phase 1: unoccluded form factors of every pair r < c of the tile; facing pairs go on the list
@@ -680,7 +687,7 @@ __global__ void __launch_bounds__(FF_THREADS, 2) k_ff_tiles(FFParams P) {
             } else {
                 // p2pFormfactor returns formfactor*visibility (float); mirrored entry by reciprocity      :165,:343
                 f_rc = fm(s_rc[rl][cl], visibility);
-                f_cr = (f_rc > 0.0f) ? fd(fm(s_gr[rl].n.w, f_rc), s_gc[cl].n.w) : 0.0f;
+                f_cr = (f_rc > 0.0f) ? fd(fm(sm.area_r[rl], f_rc), sm.area_c[cl]) : 0.0f;
             }
             if (mask == 0) { f_rc = 0.0f; f_cr = 0.0f; }
             s_rc[rl][cl] = f_rc;
@@ -745,7 +752,7 @@ __global__ void __launch_bounds__(FF_THREADS, 2) k_ff_tiles(FFParams P) {
                 const int rl = idj >> 6, cl = idj & 63;
                 const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
                 uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, nc >> 16, P.n_inner, mrq,
-                                               sm.uv, sm.perm, P.S, lane, sm.wq[tid >> 5], sm.wk[tid >> 5], sm.wb[tid >> 5]);
+                                               sm.uv, sm.perm, P.S, lane, sm.u.p2.wq[tid >> 5], sm.u.p2.wk[tid >> 5], sm.u.p2.wb[tid >> 5]);
                 if (lane == 0) finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
             }
             __syncwarp();
