@@ -258,7 +258,7 @@ def run_ours(args):
     pairs_traced = allsum(float(st["pairs_traced"]))
     rays = pairs_unique * uv.shape[0]
 
-    solver = ddist.PartitionedSolver(optixP, K, E, M, sc.mat_idx)
+    solver = ddist.PartitionedSolver(optixP, K, E, M, sc.mat_idx, fused=not args.no_fused)
     nloc = r1 - r0
 
     def one_step():
@@ -289,9 +289,10 @@ def run_ours(args):
         L.daisy_solver_last_step_ms(solver._s, C.byref(m))
         kms.append(m.value)
     k_ms = allmax(float(np.mean(kms)))
-    t_load = time.time()
-    while rank == 0 and world == 1 and len(sampler.rows) < 5 and time.time() - t_load < 3.0:
-        solver.step(False)  # keep the same load up until a few clock samples exist (short timed regions)
+    # keep the same load up for ~0.6 s so that nvidia-smi (50 ms period) sees it; the pass count is derived from the
+    # all-reduced step time, i.e. identical on every rank (the fused exchange needs all ranks to step in lockstep)
+    for _ in range(int(min(20000, max(0, 600.0 / max(ms_step, 1e-3) - args.steps)))):
+        solver.step(False)
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     alg_bytes = 4.0 * nloc * N + 16.0 * N * K  # F rows streamed once + residual in/out + B read/write
@@ -303,6 +304,14 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    # measured DRAM bytes per launch of the gather kernel (one ncu --set full capture per workload, profiles/gather_traffic.json)
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json"))).get(name)
+        if t and world == 1:
+            traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
 
     # ---- end to end through the C-ABI with HOST buffers (single GPU): H2D residual+B, pass, D2H residual+B
     e2e = None
@@ -326,15 +335,28 @@ def run_ours(args):
         e2e_s = (time.time() - t0) / nst
         e2e = {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(2 * K * N * 4), "d2h_bytes_per_step": int(2 * K * N * 4)}
     else:
-        # multi-GPU: the pass through the public API is the exchange loop itself plus reading the band sums to the host
+        # multi-GPU: every rank uploads the whole residual vector and its slice of B from pinned host memory, runs one pass
+        # through the public API (exchange included) and reads back its slices plus the band sums
+        hBl = torch.empty((K, nloc), dtype=torch.float32, pin_memory=True).numpy()
+        hRl = torch.empty((K, nloc), dtype=torch.float32, pin_memory=True).numpy()
+        hR = torch.empty((K, N), dtype=torch.float32, pin_memory=True).numpy()
+        hBl[:] = E[:, r0:r1]; hR[:] = E
+        def e2e_step():
+            _lib.check(L.daisy_solver_write_partitioned(solver._s, _lib.fptr(hBl), _lib.fptr(hR)))
+            solver.step(True)
+            _lib.check(L.daisy_solver_read(solver._s, _lib.fptr(hBl), _lib.fptr(hRl)))
+        for _ in range(2):
+            e2e_step()
+        hBl[:] = E[:, r0:r1]; hR[:] = E
         barrier()
         t0 = time.time()
         nst = min(args.steps, 50)
         for _ in range(nst):
-            solver.step(True)
+            e2e_step()
         torch.cuda.synchronize()
         e2e_s = allmax((time.time() - t0) / nst)
-        e2e = {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(8 * K * world)}
+        e2e = {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(world * (K * N + K * nloc) * 4),
+               "d2h_bytes_per_step": int(world * (2 * K * nloc * 4 + 8 * K * world))}
 
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
@@ -354,10 +376,10 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "patches": N, "bands": K, "rays_per_pair": int(uv.shape[0]), "parallelism": f"rowshard{world}",
                        "cache": "F rows per GPU %.1f GB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (4.0 * nloc * N / 1e9)},
-            "e2e": e2e, "gpu_launches": int(2 * args.steps),
+            "e2e": e2e, "gpu_launches": int((2 + (1 if K > 9 else 0) + (1 if world > 1 and not args.no_fused else 0)) * args.steps),
             "clocks": clocks,
-            "roofline": {"kernel": "k_gather_partial+k_gather_epilogue", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+            "roofline": {"kernel": ("k_gather_mma" if K > 9 else "k_gather_tma") + "+k_gather_epilogue", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes},
             "cpu_baseline": cpu_baseline,
             "formfactor": {"metric": "formfactor_visibility_rays_per_s", "value": rays / (ff_ms * 1e-3), "unit": "rays/s",
@@ -381,6 +403,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DAISY_WORKLOAD", "cornell_128k"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU form-factor sampling for the baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-gather per pass instead of the epilogue kernel's peer stores")
     ap.add_argument("--no-peer-tiles", action="store_true", help="multi-GPU: trace every tile touching this rank's rows instead of exchanging mirrored tiles")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -65,6 +65,10 @@ SYMBOLS = {
     "daisy_solver_read": (_i, [_vp, _fp, _fp]),
     "daisy_solver_write": (_i, [_vp, _fp, _fp]),
     "daisy_solver_step_local": (_i, [_vp]),
+    "daisy_solver_write_partitioned": (_i, [_vp, _fp, _fp]),
+    "daisy_solver_ipc_handles": (_i, [_vp, C.c_char_p]),
+    "daisy_solver_set_peers": (_i, [_vp, C.c_char_p, _i]),
+    "daisy_solver_step_fused": (_i, [_vp, _dp]),
     "daisy_solver_exchange_info": (_i, [_vp, C.POINTER(_vp), _i64p, _i64p]),
     "daisy_solver_step_finish": (_i, [_vp, _dp]),
     "daisy_solver_last_step_ms": (_i, [_vp, _dp]),

@@ -48,6 +48,13 @@ struct daisy_solver {
     alignas(64) CUtensorMap tmRes[2];   // exchange buffers: 3-D (n x Kp x G), box 128 x Kp x 1
     alignas(64) CUtensorMap tmFmma;     // F rows, box 32 x 128, SWIZZLE_128B
     alignas(64) CUtensorMap tmSplit;    // d_split, box 32 x 2*Kp, SWIZZLE_128B
+    // fused exchange (multi-GPU): the epilogue stores this rank's block straight into every rank's next buffer through
+    // CUDA-IPC mappings (NVLink), then raises flag[rank] = pass sequence number in every rank's flag array
+    bool fused = false;
+    float *peer_res[2][16] = { { nullptr } };          // [buffer][rank] base of that rank's exchange buffer
+    unsigned long long *peer_flags[16] = { nullptr };  // [rank] base of that rank's flag array
+    unsigned long long *d_flags = nullptr;             // own flag array (16 entries) + [16] = wait timeout marker
+    unsigned long long seq = 0;                        // passes launched since creation (never reset)
     int numpasses = 0;
     double last_ms = 0.0;
     std::vector<double> sums;   // band sums of the current residual
@@ -354,6 +361,13 @@ struct EpiParams {
     double *cta_sums;     // gridDim x K
     double *block_sums;   // K doubles in the tail of this rank's block
     unsigned int *done;
+    // fused exchange: npeers > 0 => the block (and its band sums) go to peer_out[g] / peer_sums[g] of every rank g
+    // (own rank included) and, once every CTA's stores are fenced, flag[rank] of every rank is set to seq
+    int npeers;
+    float *peer_out[16];
+    double *peer_sums[16];
+    unsigned long long *peer_flag[16];
+    unsigned long long seq;
 };
 
 template <int K>
@@ -380,7 +394,11 @@ __global__ void __launch_bounds__(256) k_gather_epilogue(EpiParams P) {
             float y = 0.0f;
 #pragma unroll
             for (int j = 0; j < K; j++) y = fmaf(Mp[j * K + k], b[j], y);
-            P.res_out_block[(size_t)k * P.n + row] = y;                          // residualvector[j][i] = result[j]
+            if (P.npeers > 0) {
+                for (int g = 0; g < P.npeers; g++) P.peer_out[g][(size_t)k * P.n + row] = y; // NVLink stores into every rank's buffer
+            } else {
+                P.res_out_block[(size_t)k * P.n + row] = y;                      // residualvector[j][i] = result[j]
+            }
             P.B[(size_t)k * P.n + row] = P.B[(size_t)k * P.n + row] + y;         // lightningvalues += residual   :221-223
             loc[k] += (double)y;
         }
@@ -398,7 +416,7 @@ __global__ void __launch_bounds__(256) k_gather_epilogue(EpiParams P) {
         for (int w = 0; w < 8; w++) v += s_sum[w][tid];
         P.cta_sums[(size_t)blockIdx.x * K + tid] = v;
     }
-    __threadfence();
+    if (P.npeers > 0) __threadfence_system(); else __threadfence(); // peer stores must be visible before the flag below
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(P.done, 1u) == gridDim.x - 1);
     __syncthreads();
@@ -408,9 +426,36 @@ __global__ void __launch_bounds__(256) k_gather_epilogue(EpiParams P) {
             double v = 0.0;
             volatile const double *cs = P.cta_sums;
             for (unsigned b = 0; b < gridDim.x; b++) v += cs[(size_t)b * K + tid];
-            P.block_sums[tid] = v;
+            if (P.npeers > 0) { for (int g = 0; g < P.npeers; g++) P.peer_sums[g][tid] = v; }
+            else P.block_sums[tid] = v;
         }
         if (tid == 0) *P.done = 0;
+        if (P.npeers > 0) {
+            __threadfence_system();
+            __syncthreads();
+            if (tid < P.npeers) {
+                // release: every store of this kernel (fenced by each CTA before it arrived on `done`) precedes the flag
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.peer_flag[tid]), "l"(P.seq) : "memory");
+            }
+        }
+    }
+}
+
+// waits until every rank's block of pass `seq` has arrived in this rank's buffer (flag[g] >= seq for all g); gives up
+// after ~2 s so that a dead peer turns into an error instead of a hung GPU
+__global__ void k_wait_flags(unsigned long long *flags, int G, unsigned long long seq) {
+    const int g = threadIdx.x;
+    if (g >= G) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    while (true) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + g) : "memory");
+        if (v >= seq) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) { flags[16] = seq; break; }
+        __nanosleep(200);
     }
 }
 
@@ -474,6 +519,16 @@ static int launch_pass_K(daisy_solver *s) {
     E.partial = s->d_partial; E.nsplit = s->nsplit; E.nloc = s->nloc; E.n = s->n;
     E.M = s->d_M; E.mat = s->d_mat; E.res_out_block = next; E.B = s->d_B;
     E.cta_sums = s->d_cta_sums; E.block_sums = reinterpret_cast<double *>(next + s->sums_off); E.done = s->d_done;
+    E.npeers = 0; E.seq = s->seq;
+    if (s->fused) {
+        E.npeers = s->G;
+        for (int g = 0; g < s->G; g++) {
+            float *blk = s->peer_res[s->cur ^ 1][g] + (size_t)s->rank * s->bstride;
+            E.peer_out[g] = blk;
+            E.peer_sums[g] = reinterpret_cast<double *>(blk + s->sums_off);
+            E.peer_flag[g] = s->peer_flags[g] + s->rank;
+        }
+    }
     int egrid = (s->nloc + 255) / 256;
     if (egrid > 148) egrid = 148;
     if (egrid < 1) egrid = 1;
@@ -593,6 +648,14 @@ static int padded_K(int K) { return K <= 1 ? 1 : K <= 3 ? 3 : K <= 9 ? 9 : K <= 
 
 static void free_solver(daisy_solver *s) {
     if (!s) return;
+    if (s->fused)
+        for (int g = 0; g < s->G; g++) {
+            if (g == s->rank) continue;
+            if (s->peer_res[0][g]) cudaIpcCloseMemHandle(s->peer_res[0][g]);
+            if (s->peer_res[1][g]) cudaIpcCloseMemHandle(s->peer_res[1][g]);
+            if (s->peer_flags[g]) cudaIpcCloseMemHandle(s->peer_flags[g]);
+        }
+    cudaFree(s->d_flags);
     cudaFree(s->d_res[0]); cudaFree(s->d_res[1]); cudaFree(s->d_B); cudaFree(s->d_E); cudaFree(s->d_M); cudaFree(s->d_mat);
     cudaFree(s->d_partial); cudaFree(s->d_cta_sums); cudaFree(s->d_done); cudaFree(s->d_split);
     if (s->e0) cudaEventDestroy(s->e0);
@@ -652,6 +715,8 @@ extern "C" int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const 
     SC(cudaMalloc(&s->d_cta_sums, sizeof(double) * 148 * s->Kp));
     SC(cudaMalloc(&s->d_done, sizeof(unsigned int)));
     SC(cudaMemset(s->d_done, 0, sizeof(unsigned int)));
+    SC(cudaMalloc(&s->d_flags, sizeof(unsigned long long) * 17));
+    SC(cudaMemset(s->d_flags, 0, sizeof(unsigned long long) * 17));
     SC(cudaMemset(s->d_res[0], 0, exb));
     SC(cudaMemset(s->d_res[1], 0, exb));
     SC(cudaEventCreate(&s->e0));
@@ -692,6 +757,8 @@ extern "C" int daisy_solver_reset(daisy_solver *s) {
     DZ_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
     size_t exb = sizeof(float) * (size_t)s->G * s->bstride;
+    // fused exchange: a slower rank may still be storing its block of the last pass into this rank's buffers
+    if (s->fused && s->seq > 0) k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq);
     // residualvector = emission; lightningvalues = emission                                 Lightning.h:159-165
     s->cur = 0;
     DZ_CUDA(cudaMemcpyAsync(s->d_res[0], s->d_E, exb, cudaMemcpyDeviceToDevice, st));
@@ -725,11 +792,18 @@ extern "C" int daisy_solver_exchange_info(daisy_solver *s, void **d_next_buffer,
 static int fetch_sums(daisy_solver *s) {
     // per-rank partial band sums sit in the tail of every block of the current buffer
     cudaStream_t st = s->ctx->stream;
+    unsigned long long timed_out = 0;
+    if (s->fused) {
+        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq); // every rank's block of the last pass has landed
+        DZ_CUDA(cudaGetLastError());
+        DZ_CUDA(cudaMemcpyAsync(&timed_out, s->d_flags + 16, sizeof(timed_out), cudaMemcpyDeviceToHost, st));
+    }
     std::vector<double> tails((size_t)s->G * s->Kp);
     for (int g = 0; g < s->G; g++)
         DZ_CUDA(cudaMemcpyAsync(&tails[(size_t)g * s->Kp], s->d_res[s->cur] + (size_t)g * s->bstride + s->sums_off,
                                 sizeof(double) * s->Kp, cudaMemcpyDeviceToHost, st));
     DZ_CUDA(cudaStreamSynchronize(st));
+    if (timed_out) { daisy_set_error("fused exchange: a peer's block of pass %llu did not arrive within 2 s", timed_out); return DAISY_E_STATE; }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s->e0, s->e1) == cudaSuccess) s->last_ms = ms;
     s->sums.assign(s->K, 0.0);
@@ -762,6 +836,57 @@ extern "C" int daisy_solver_step(daisy_solver *s, double *band_sums) {
     DZ_REQUIRE(s->G == 1, DAISY_E_STATE, "daisy_solver_step: partitioned solver needs step_local / exchange / step_finish");
     int rc = daisy_solver_step_local(s);
     if (rc) return rc;
+    return daisy_solver_step_finish(s, band_sums);
+}
+
+// ---- fused exchange over peer memory (multi-GPU, one process per GPU) ------------------------------------------
+extern "C" int daisy_solver_ipc_handles(daisy_solver *s, void *handles192) {
+    DZ_REQUIRE(s && handles192, DAISY_E_INVALID, "daisy_solver_ipc_handles: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    cudaIpcMemHandle_t h[3];
+    DZ_CUDA(cudaIpcGetMemHandle(&h[0], s->d_res[0]));
+    DZ_CUDA(cudaIpcGetMemHandle(&h[1], s->d_res[1]));
+    DZ_CUDA(cudaIpcGetMemHandle(&h[2], s->d_flags));
+    memcpy(handles192, h, sizeof(h));
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_set_peers(daisy_solver *s, const void *handles, int nranks) {
+    DZ_REQUIRE(s && handles, DAISY_E_INVALID, "daisy_solver_set_peers: null argument");
+    DZ_REQUIRE(nranks == s->G && nranks <= 16, DAISY_E_INVALID, "daisy_solver_set_peers: nranks must match the partition (<= 16)");
+    DZ_REQUIRE(!s->fused, DAISY_E_STATE, "daisy_solver_set_peers: peers already set");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    for (int g = 0; g < nranks; g++) {
+        if (g == s->rank) { s->peer_res[0][g] = s->d_res[0]; s->peer_res[1][g] = s->d_res[1]; s->peer_flags[g] = s->d_flags; continue; }
+        cudaIpcMemHandle_t h[3];
+        memcpy(h, (const char *)handles + (size_t)g * sizeof(h), sizeof(h));
+        void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+        DZ_CUDA(cudaIpcOpenMemHandle(&p0, h[0], cudaIpcMemLazyEnablePeerAccess));
+        DZ_CUDA(cudaIpcOpenMemHandle(&p1, h[1], cudaIpcMemLazyEnablePeerAccess));
+        DZ_CUDA(cudaIpcOpenMemHandle(&p2, h[2], cudaIpcMemLazyEnablePeerAccess));
+        s->peer_res[0][g] = (float *)p0; s->peer_res[1][g] = (float *)p1; s->peer_flags[g] = (unsigned long long *)p2;
+    }
+    s->fused = true;
+    return DAISY_OK;
+}
+
+// one pass with the exchange fused into the epilogue kernel: wait for the blocks of the previous pass, gather, store
+// this rank's new block into every rank's next buffer and raise the flags.  No host synchronisation, no NCCL call.
+extern "C" int daisy_solver_step_fused(daisy_solver *s, double *band_sums) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_step_fused: null solver");
+    DZ_REQUIRE(s->fused, DAISY_E_STATE, "daisy_solver_step_fused: call daisy_solver_set_peers first");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    DZ_CUDA(cudaEventRecord(s->e0, st));
+    if (s->seq > 0) {
+        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq);
+        DZ_CUDA(cudaGetLastError());
+    }
+    s->seq++;
+    int rc = launch_pass(s);
+    if (rc) return rc;
+    DZ_CUDA(cudaEventRecord(s->e1, st));
     return daisy_solver_step_finish(s, band_sums);
 }
 
@@ -822,6 +947,27 @@ extern "C" int daisy_solver_write(daisy_solver *s, const float *B, const float *
                               cudaMemcpyHostToDevice, st));
     DZ_CUDA(cudaStreamSynchronize(st));
     compute_sums_from_host(s, residual);
+    s->sums_valid = true;
+    return DAISY_OK;
+}
+
+// partitioned counterpart of daisy_solver_write: B_local is K x nloc (this rank's rows), residual_full is K x N (every
+// rank holds the whole residual vector, as after an exchange)
+extern "C" int daisy_solver_write_partitioned(daisy_solver *s, const float *B_local, const float *residual_full) {
+    DZ_REQUIRE(s && B_local && residual_full, DAISY_E_INVALID, "daisy_solver_write_partitioned: null argument");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    if (s->fused && s->seq > 0) k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq); // peers' stores of the last pass have landed
+    if (s->nloc > 0)
+        DZ_CUDA(cudaMemcpy2DAsync(s->d_B, sizeof(float) * s->n, B_local, sizeof(float) * s->nloc, sizeof(float) * s->nloc, s->K, cudaMemcpyHostToDevice, st));
+    for (int g = 0; g < s->G; g++) {
+        const int c0 = g * s->n, w = (c0 < s->N) ? ((s->N - c0 < s->n) ? s->N - c0 : s->n) : 0;
+        if (w > 0)
+            DZ_CUDA(cudaMemcpy2DAsync(s->d_res[s->cur] + (size_t)g * s->bstride, sizeof(float) * s->n, residual_full + c0, sizeof(float) * s->N,
+                                      sizeof(float) * w, s->K, cudaMemcpyHostToDevice, st));
+    }
+    DZ_CUDA(cudaStreamSynchronize(st));
+    compute_sums_from_host(s, residual_full);
     s->sums_valid = true;
     return DAISY_OK;
 }

@@ -91,7 +91,11 @@ class _DevMem:
 class PartitionedSolver:
     """A ``daisy_solver`` driven through the multi-GPU entry points with torch.distributed doing the exchange."""
 
-    def __init__(self, optixP, K, E, M, mat_idx, group=None):
+    def __init__(self, optixP, K, E, M, mat_idx, group=None, fused: bool = True):
+        """``fused=True`` (default with more than one rank): the exchange is done by the epilogue kernel itself -- it
+        stores this rank's block into every rank's next buffer through CUDA-IPC mappings over NVLink and raises
+        per-rank flags the next pass waits on (``daisy_solver_step_fused``).  ``fused=False``: local kernels + one
+        in-place NCCL all-gather per pass (``exchange_pass``)."""
         import torch
         self.torch = torch
         self.p = optixP
@@ -104,6 +108,16 @@ class PartitionedSolver:
         _lib.check(L.daisy_solver_create(optixP._ctx, K, _lib.fptr(E), _lib.fptr(M), M.shape[0], _lib.iptr(mat), C.byref(self._s)),
                    "solver_create")
         self._views = {}
+        self.fused = bool(fused) and self.nranks > 1
+        if self.fused:
+            import torch.distributed as tdist
+            h = C.create_string_buffer(192)
+            _lib.check(L.daisy_solver_ipc_handles(self._s, h), "solver_ipc_handles")
+            handles = [None] * self.nranks
+            tdist.all_gather_object(handles, bytes(h.raw), group=group)
+            blob = C.create_string_buffer(b"".join(handles), 192 * self.nranks)
+            _lib.check(L.daisy_solver_set_peers(self._s, blob, self.nranks), "solver_set_peers")
+            tdist.barrier(group=group)  # every rank has mapped every buffer before the first remote store
 
     def _next_view(self):
         L = _lib.lib()
@@ -115,6 +129,13 @@ class PartitionedSolver:
 
     def step(self, want_sums: bool = False):
         L = _lib.lib()
+        if self.fused:
+            if want_sums:
+                sums = np.zeros(self.K, np.float64)
+                _lib.check(L.daisy_solver_step_fused(self._s, sums.ctypes.data_as(C.POINTER(C.c_double))), "step_fused")
+                return sums
+            _lib.check(L.daisy_solver_step_fused(self._s, None), "step_fused")
+            return None
         buf = self._next_view()
         exchange_pass(lambda: _lib.check(L.daisy_solver_step_local(self._s), "step_local"), buf, self.rank, self.nranks, self.group)
         if want_sums:
@@ -151,6 +172,10 @@ class PartitionedSolver:
         return B, R
 
     def close(self):
+        if self._s and self.fused:
+            import torch.distributed as tdist
+            self.torch.cuda.synchronize()
+            tdist.barrier(group=self.group)  # no rank unmaps while a peer may still be storing into its buffers
         if self._s:
             _lib.lib().daisy_solver_destroy(self._s)
             self._s = None

@@ -145,6 +145,18 @@ int daisy_solver_step_finish(daisy_solver *s, double *band_sums);
 /* timing of the last step: device milliseconds of the gather kernel (CUDA events on the context's stream) */
 int daisy_solver_last_step_ms(daisy_solver *s, double *ms);
 
+/* Fused exchange (replaces the NCCL all-gather of the loop above when all ranks sit in one NVLink domain):
+ *   daisy_solver_ipc_handles: 3 x 64-byte CUDA-IPC handles of this rank's two exchange buffers and its flag array
+ *   daisy_solver_set_peers  : the handles of all ranks, rank-major (nranks x 192 bytes), gathered by the caller
+ *   daisy_solver_step_fused : one pass; the epilogue kernel stores this rank's block (K x n floats + K band sums) into
+ *                             every rank's next buffer over NVLink and raises per-rank flags; the next pass waits on
+ *                             the flags on the device.  Same results as step_local / all-gather / step_finish. */
+/* partitioned daisy_solver_write: B_local = K x (row1-row0), residual_full = K x N (whole vector on every rank) */
+int daisy_solver_write_partitioned(daisy_solver *s, const float *B_local, const float *residual_full);
+int daisy_solver_ipc_handles(daisy_solver *s, void *handles192);
+int daisy_solver_set_peers(daisy_solver *s, const void *handles, int nranks);
+int daisy_solver_step_fused(daisy_solver *s, double *band_sums);
+
 #ifdef __cplusplus
 }
 #endif
