@@ -329,3 +329,78 @@ def test_trace_screen_matches_literal_restatement(dz, cornell2048, uv50):
     assert (img > 0).mean() > 0.15  # the box fills a good part of the frame
     assert np.allclose(img, want, rtol=1e-5, atol=2e-6)
     p.close()
+
+
+def test_coplanar_skipping_changes_nothing(dz, uv50, monkeypatch):
+    """Coplanar skipping (formfactor.cu: k_tri_planes / shaft_candidates) is a pure optimisation: with it switched off
+    (DAISY_FF_RING=0) every triangle of a candidate list is tested by every sample.  Matrix and masks must be identical
+    bit for bit at a size where most pairs take the skipping path."""
+    from daisyriot_b200 import scenes
+    sc = scenes.cornell_box(8192)
+    got = {}
+    for ring in ("1", "0"):
+        monkeypatch.setenv("DAISY_FF_RING", ring)
+        p = _ctx(dz, sc, uv50)
+        got[ring] = (p.cudaCalculateRadiosityMatrix().rows().copy(), p.visibilityMasks(3000, 256).copy())
+        p.close()
+    assert np.array_equal(got["1"][0].view(np.uint32), got["0"][0].view(np.uint32))
+    assert np.array_equal(got["1"][1], got["0"][1])
+
+
+def test_edge_heavy_pattern_and_coplanar_decal_vs_bruteforce(dz):
+    """Stress for the skipping premises, against the brute-force oracle (every ray against every triangle):
+    * a sample pattern with samples ON the triangle edges and vertices (u = 0, v = 0, u + v = 1) next to random ones --
+      edge samples must still test the coplanar neighbours;
+    * a decal: two triangles lying IN the floor plane and overlapping floor patches -- k_tri_planes must disqualify the
+      patches they overlap, because a ray leaving such a patch can start inside the decal."""
+    from daisyriot_b200 import scenes
+    from daisyriot_b200.scenes import Scene
+    base = scenes.cornell_box(512)
+    V = np.concatenate([base.vertices, np.array([[1.0, 0.0, 3.0], [2.1, 0.0, 3.0], [1.0, 0.0, 4.3], [2.1, 0.0, 4.3]], np.float32)])
+    nv0, nn0 = len(base.vertices), len(base.normals)
+    VN = np.concatenate([base.normals, np.array([[0, 1, 0]], np.float32)])
+    T = np.concatenate([base.tri, np.array([[nv0, nv0 + 2, nv0 + 1, nn0, nn0, nn0], [nv0 + 1, nv0 + 2, nv0 + 3, nn0, nn0, nn0]], np.int32)])
+    sc = Scene(V, VN, T, np.concatenate([base.mat_idx, [3, 3]]).astype(np.int32), base.materials, "cornell512_decal")
+    rng = np.random.RandomState(11)
+    u = rng.uniform(0, 1, 50).astype(np.float32)
+    v = (rng.uniform(0, 1, 50).astype(np.float32) * (1 - u)).astype(np.float32)
+    u[:6] = [0, 0, 1, 0.5, 0.25, 0]
+    v[:6] = [0, 1, 0, 0.5, 0, 0.75]
+    uv = np.stack([u, v], 1).astype(np.float32)
+    p = _ctx(dz, sc, uv)
+    F = p.cudaCalculateRadiosityMatrix().rows()
+    masks = p.visibilityMasks()
+    F_ref, masks_ref, _ = _oracle(sc).radmat_rows(uv, 0, sc.numtriangles, brute=True)
+    assert np.array_equal(masks, masks_ref)
+    assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
+    p.close()
+
+
+def test_gather_tensor_core_path_at_scale(dz, uv50):
+    """K = 32 on the tcgen05 3xTF32 path with 8192 columns per row (256 accumulator drains per item): the truncating
+    tensor-core accumulator must not show up as a bias -- 1e-5 relative against the FP64-accumulating oracle, and the
+    band sums (which expose any systematic bias directly) within 2e-6."""
+    from daisyriot_b200 import _lib, scenes
+    from oracle import pyoracle
+    sc = scenes.cornell_box(8192)
+    p = _ctx(dz, sc, uv50)
+    N, K = sc.numtriangles, 32
+    rng = np.random.RandomState(5)
+    F = (rng.uniform(0, 1, (N, N)).astype(np.float32) * (rng.uniform(0, 1, (N, N)) < 0.3) / N).astype(np.float32)
+    np.fill_diagonal(F, 0)
+    p.loadRadiosityMatrix(F)
+    M = rng.uniform(0, 0.06, (len(sc.materials), K, K)).astype(np.float32)
+    E = np.ascontiguousarray(rng.uniform(0, 3, (K, N)).astype(np.float32))
+    s = _solver(dz, p, K, E, M, sc.mat_idx)
+    L = _lib.lib()
+    res, B = E.copy(), E.copy()
+    for it in range(2):
+        sums = np.zeros(K)
+        _lib.check(L.daisy_solver_step(s, sums.ctypes.data_as(C.POINTER(C.c_double))))
+        sums_ref = pyoracle.gather_pass(F, res, B, M, sc.mat_idx, accum=1)
+        Bg, Rg = np.empty_like(E), np.empty_like(E)
+        _lib.check(L.daisy_solver_read(s, _lib.fptr(Bg), _lib.fptr(Rg)))
+        assert np.allclose(Rg, res, rtol=1e-5, atol=1e-5 * np.abs(res).max()), (it, np.abs(Rg - res).max())
+        assert np.allclose(sums, sums_ref, rtol=2e-6), (it, np.abs(sums / sums_ref - 1).max())
+    L.daisy_solver_destroy(s)
+    p.close()
