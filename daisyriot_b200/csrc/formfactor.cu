@@ -827,16 +827,15 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     if (r1 <= r0 && !(write_F && ctx->peers_set)) return DAISY_OK;
     int t0 = r0 / TILE, t1 = (r1 - 1) / TILE; // tiles overlapping the range
     // jobs: upper-triangle tiles (R <= C).  Local mode: every tile with R or C inside this context's rows [t0, t1]
-    // (off-diagonal blocks are then traced by both owners).  Peer mode: every tile is assigned to exactly one rank --
-    // tiles inside one rank's block to that rank, tiles between ranks a < b alternately to a and b (checkerboard).
+    // (off-diagonal blocks are then traced by both owners).  Peer mode: every tile is traced by exactly one rank, chosen by a
+    // hash of (R, C) -- any rank can store a tile and its mirror into the two owners' matrices through the IPC mappings, and
+    // tile cost varies by orders of magnitude with the geometry (wall-to-wall blocks vs blocks of one plane), so spreading
+    // the ~ntiles^2/2 tiles pseudo-randomly is what balances the ranks (owner-based assignment left 8 GPUs at 4.5x).
     const bool peer = write_F && ctx->peers_set && ctx->nranks > 1;
-    const int tiles_per_rank = ctx->rows_per_rank / TILE;
     auto mine = [&](int R, int C) -> bool {
         if (!peer) return (R >= t0 && R <= t1) || (C >= t0 && C <= t1);
-        int a = R / tiles_per_rank, b = C / tiles_per_rank;
-        if (a == b) return a == ctx->rank;
-        if (a != ctx->rank && b != ctx->rank) return false;
-        return (((R + C) & 1) == 0) ? (ctx->rank == a) : (ctx->rank == b);
+        const uint32_t h = ((uint32_t)R * 0x9E3779B1u) ^ ((uint32_t)C * 0x85EBCA77u);
+        return (int)((h >> 12) % (uint32_t)ctx->nranks) == ctx->rank;
     };
     size_t njobs = 0;
     for (int R = 0; R < ntiles; R++)
