@@ -10,7 +10,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libdaisy_b200.so")
+SO_PATH = os.environ.get("DAISY_B200_LIB") or os.path.join(_HERE, "libdaisy_b200.so")  # override: A/B builds of the library
 CSRC = os.path.join(_HERE, "csrc")
 
 HIT_DTYPE = np.dtype([("t", np.float32), ("triangleId", np.int32), ("u", np.float32), ("v", np.float32)])

@@ -32,6 +32,11 @@
 #define MM_ND 4     // TMEM accumulator buffers (one stage each)
 #define MM_THREADS 512
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -133,13 +138,14 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     unsigned char *base = mm_smem_raw + (((raw + 1023u) & ~1023u) - raw); // SWIZZLE_128B tiles need 1024-byte alignment
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)MM_NS * STAGE);
     uint64_t *full = bars, *empty = bars + MM_NS, *a_full = bars + 2 * MM_NS, *a_empty = a_full + MM_NA;
-    uint64_t *d_full = a_empty + MM_NA, *d_empty = d_full + MM_ND;
+    uint64_t *mma_done = a_empty + MM_NA, *d_empty = mma_done + MM_NS; // a_empty is unused (mma_done serves it)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_empty + MM_ND);
+    static_assert(MM_NS == 4 && MM_NA == 2 && MM_ND == 4, "mma_done ring indexing below assumes these depths");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < MM_NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 5); }  // 4 converter warps + the MMA commit
+        for (int i = 0; i < MM_NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); mbar_init(&mma_done[i], 1); }  // empty: 4 converter warps
         for (int i = 0; i < MM_NA; i++) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < MM_ND; i++) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+        for (int i = 0; i < MM_ND; i++) mbar_init(&d_empty[i], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -162,7 +168,8 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                 const int nstep = (c_end - c_begin + MM_COLS - 1) / MM_COLS;
                 for (int s = 0; s < nstep; s++, it++) {
                     const int st = it % MM_NS;
-                    mbar_wait(&empty[st], ((it / MM_NS) & 1) ^ 1);
+                    mbar_wait(&empty[st], ((it / MM_NS) & 1) ^ 1);      // converters have read the F tiles of stage it-4
+                    mbar_wait(&mma_done[st], ((it / MM_NS) & 1) ^ 1);   // the MMAs of stage it-4 have read its band tiles
                     unsigned char *sf = base + (size_t)st * STAGE;
                     const int c0 = c_begin + s * MM_COLS;
                     mbar_expect_tx(&full[st], (uint32_t)STAGE);
@@ -175,30 +182,34 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
         }
     } else if (warp == 1) {
         // ------------------------------- MMA issuer ---------------------------------
-        if (lane == 0) {
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int split = item % P.nsplit;
-                const int c_begin = split * P.colw, c_end = min(P.ncols, c_begin + P.colw);
-                const int nstep = (c_end - c_begin + MM_COLS - 1) / MM_COLS;
-                for (int s = 0; s < nstep; s++, it++) {
-                    const int st = it % MM_NS, a = it % MM_NA, b = it % MM_ND;
-                    mbar_wait(&full[st], (it / MM_NS) & 1);
-                    mbar_wait(&a_full[a], (it / MM_NA) & 1);
-                    mbar_wait(&d_empty[b], ((it / MM_ND) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(base + (size_t)st * STAGE + B_OFF);
-                    const uint32_t a_tmem = tmem + A_COL0 + a * A_COLS;
-                    const uint32_t d_tmem = tmem + b * DCOLS;
+        // The whole warp runs the loop (uniform control flow keeps descriptors in uniform registers); one elected lane
+        // issues.  The issuing thread is the critical path of this kernel (per-MMA issue ~40 clk plus the barrier
+        // round trips), so it waits on two barriers per stage and signals one: a_full[a] implies full[st] (the
+        // converters waited on it), and a single commit per stage serves the producer (smem slot), the converters
+        // (operand slot) and the epilogue (accumulator ready).
+        const bool leader = elect_one();
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int split = item % P.nsplit;
+            const int c_begin = split * P.colw, c_end = min(P.ncols, c_begin + P.colw);
+            const int nstep = (c_end - c_begin + MM_COLS - 1) / MM_COLS;
+            for (int s = 0; s < nstep; s++, it++) {
+                const int st = it % MM_NS, a = it % MM_NA, b = it % MM_ND;
+                mbar_wait(&a_full[a], (it / MM_NA) & 1);
+                mbar_wait(&d_empty[b], ((it / MM_ND) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(base + (size_t)st * STAGE + B_OFF);
+                const uint32_t a_tmem = tmem + A_COL0 + a * A_COLS;
+                const uint32_t d_tmem = tmem + b * DCOLS;
+                if (leader) {
 #pragma unroll
                     for (int k = 0; k < MM_COLS / 8; k++) {
                         const uint64_t bdesc = tc_smem_desc_sw128(b_addr + (k >> 2) * B_SUB + (k & 3) * 32);
                         tc_mma_tf32_ts(d_tmem, a_tmem + k * 8, bdesc, IDESC_2K, k > 0 ? 1u : 0u);        // Fh x [Rh;Rl]
                         tc_mma_tf32_ts(d_tmem, a_tmem + MM_COLS + k * 8, bdesc, IDESC_K, 1u);          // Fl x Rh
                     }
-                    tc_commit(&empty[st]);
-                    tc_commit(&a_empty[a]);
-                    tc_commit(&d_full[b]);
+                    tc_commit(&mma_done[it % MM_NS]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < 12) {
@@ -237,7 +248,7 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                         if (lane == 0) mbar_arrive(&empty[st]);     // both F sub-tiles are in registers
                     }
                     if (sub == 0) {
-                        mbar_wait(&a_empty[a], ((it / MM_NA) & 1) ^ 1);
+                        if (it >= MM_NA) mbar_wait(&mma_done[(it - MM_NA) % MM_NS], ((it - MM_NA) / MM_NS) & 1); // MMAs of stage it-2 are done with this operand slot
                         tc_fence_after();
                     }
                     tc_st32(a_tmem + sub * MM_SUB, hi);
@@ -262,7 +273,7 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
             for (int k = 0; k < K; k++) out[k] = 0.0f;
             for (int s = 0; s < nstep; s++, it++) {
                 const int b = it % MM_ND;
-                mbar_wait(&d_full[b], (it / MM_ND) & 1);
+                mbar_wait(&mma_done[it % MM_NS], (it / MM_NS) & 1);
                 tc_fence_after();
                 if constexpr (K == 32) {
                     uint32_t r0[32], r1[32];
