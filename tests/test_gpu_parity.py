@@ -404,3 +404,28 @@ def test_gather_tensor_core_path_at_scale(dz, uv50):
         assert np.allclose(sums, sums_ref, rtol=2e-6), (it, np.abs(sums / sums_ref - 1).max())
     L.daisy_solver_destroy(s)
     p.close()
+
+
+@pytest.mark.parametrize("S,kind", [(7, "random"), (64, "random"), (33, "all_inner"), (20, "all_edge")])
+def test_sample_counts_and_inner_edge_splits_vs_bruteforce(dz, cornell512, S, kind):
+    """Sample counts other than 50 (one pass, two full passes, a one-lane second pass) and patterns that are all inner
+    or all edge samples: masks (bit position = the caller's sample index) and matrix against the brute-force oracle."""
+    rng = np.random.RandomState(100 + S)
+    if kind == "all_inner":
+        u = rng.uniform(0.05, 0.4, S)
+        v = rng.uniform(0.05, 0.4, S)
+    elif kind == "all_edge":
+        u = rng.uniform(0, 1, S)
+        v = (1 - u) * rng.choice([0.0, 0.003, 0.999], S)
+    else:
+        u = rng.uniform(0, 1, S)
+        v = rng.uniform(0, 1, S) * (1 - u)
+    uv = np.stack([u, v], 1).astype(np.float32)
+    sc = cornell512
+    p = _ctx(dz, sc, uv)
+    F = p.cudaCalculateRadiosityMatrix().rows()
+    masks = p.visibilityMasks()
+    F_ref, masks_ref, _ = _oracle(sc).radmat_rows(uv, 0, sc.numtriangles, brute=True)
+    assert np.array_equal(masks, masks_ref)
+    assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
+    p.close()
