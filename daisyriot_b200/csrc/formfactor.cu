@@ -316,7 +316,8 @@ __device__ __noinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const T
 // direction between the two centroids.  Skipping any axis only makes the test say "may intersect" more often, so the
 // candidate list is always a superset of the triangles any of the S rays can touch; rays are then tested against the
 // list with the very same watertight routine and the same (t, id) rule => identical masks, far fewer node visits.
-#define FF_QCAP 8 // pending watertight tests per lane
+#define FF_QCAP 6 // pending watertight tests per lane
+#define HEAVY_CAP 1024 // deferred per-ray-walk pairs per tile; beyond that they are resolved on the spot
 #define SHAFT_CAP 256 // ints of global scratch per pair slot; longer lists fall back to per-ray LBVH walks
 struct Shaft {
     float lox, loy, loz, hix, hiy, hiz; // hull AABB
@@ -475,10 +476,10 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         };
         {
             bool any_alive = __any_sync(0xffffffffu, alive);
-            for (int c0 = 0; c0 < n_main && any_alive; c0 += 32) {
-                // stage 32 candidates (id + padded box) in the warp's shared-memory slot: the list was written by another lane
+            for (int c0 = 0; c0 < n_main && any_alive; c0 += 16) {
+                // stage 16 candidates (id + padded box) in the warp's shared-memory slot: the list was written by another lane
                 // of this warp, so it is read through L2 (ld.global.cg); the boxes are then broadcast LDS.128 in the loop
-                const int nb = min(32, n_main - c0);
+                const int nb = min(16, n_main - c0);
                 __syncwarp();
                 if (lane < nb) {
                     const int k = __ldcg(cand + c0 + lane);
@@ -577,8 +578,8 @@ struct FFSmem {
         struct { PatchGeom gr[TILE], gc[TILE]; } p1;
         struct {
             int wq[FF_THREADS / 32][FF_QCAP * 32];
-            int wk[FF_THREADS / 32][32];
-            float4 wb[FF_THREADS / 32][64];
+            int wk[FF_THREADS / 32][16];
+            float4 wb[FF_THREADS / 32][32];
         } p2;
     } u;
     float area_r[TILE], area_c[TILE]; // patch areas (needed after phase 1 by the host-variant reciprocity rule)
@@ -588,7 +589,7 @@ struct FFSmem {
     float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
     float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
     unsigned short list[TILE * TILE];
-    unsigned short heavy[TILE * TILE];
+    unsigned short heavy[HEAVY_CAP];
     int nlist, next, job, nown, nheavy, hnext;
     float uv[2 * DAISY_MAX_SAMPLES];
 };
@@ -740,7 +741,16 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                     m_req = fmaxf(rl_.on ? mlo : 0.f, rh_.on ? mhi : 0.f);
                 }
                 ncand = shaft_candidates(P.nodes, P.tv, P.root, sh, rl_, rh_, P.tau, R0 + rl, C0 + cl, my_cand);
-                if (ncand < 0) s_heavy[atomicAdd(&s_nheavy, 1)] = (unsigned short)idx;
+                if (ncand < 0) {
+                    const int h = atomicAdd(&s_nheavy, 1);
+                    if (h < HEAVY_CAP) s_heavy[h] = (unsigned short)idx;
+                    else { // deferral list full (never seen on the benchmark scenes): walk the LBVH per ray right here
+                        uint64_t mask = 0;
+                        for (int i = 0; i < P.S; i++)
+                            if (ray_sees(P.nodes, P.tv, P.root, A, B, R0 + rl, C0 + cl, c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
+                        finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
+                    }
+                }
             }
             __syncwarp();
             // (ii) lane = sample: the warp resolves its 32 pairs one after the other
@@ -758,8 +768,8 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
             __syncwarp();
         }
         __syncthreads();
-        const int nheavy = s_nheavy;
-        if (tid == 0 && nheavy) atomicAdd(P.pair_counter + 2, (unsigned long long)nheavy);
+        const int nheavy = min(s_nheavy, HEAVY_CAP);
+        if (tid == 0 && s_nheavy) atomicAdd(P.pair_counter + 2, (unsigned long long)s_nheavy);
         while (true) { // 2b
             int q0 = 0;
             if (lane == 0) q0 = atomicAdd(&s_hnext, 32);
