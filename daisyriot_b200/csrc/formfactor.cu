@@ -24,6 +24,9 @@
 #define EDGE_MARGIN 0.02f
 __constant__ float c_uv[2 * DAISY_MAX_SAMPLES];
 __constant__ int c_perm[DAISY_MAX_SAMPLES];
+#ifdef DAISY_FF_STATS
+__device__ unsigned long long g_ffstats[32];
+#endif
 
 int dz_set_samples_const(daisy_ctx *ctx) {
     float uv[2 * DAISY_MAX_SAMPLES] = { 0 };
@@ -474,6 +477,9 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
             }
             qlen = 0;
         };
+#ifdef DAISY_FF_STATS
+        int dbg_iters = 0;
+#endif
         {
             bool any_alive = __any_sync(0xffffffffu, alive);
             for (int c0 = 0; c0 < n_main && any_alive; c0 += 16) {
@@ -497,6 +503,9 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                             if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { wq[qlen * 32 + lane] = wk[j]; qlen++; }
                         }
                     }
+#ifdef DAISY_FF_STATS
+                    dbg_iters += min(FF_QCAP, nb - j0);
+#endif
                     flush(); // at most FF_QCAP entries were queued since the last flush
                     any_alive = __any_sync(0xffffffffu, alive);
                     if (!any_alive) break;
@@ -534,6 +543,9 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 if (__any_sync(0xffffffffu, hit) && lane == e) alive = false;
             }
         }
+#ifdef DAISY_FF_STATS
+        if (lane == 0) atomicAdd(&g_ffstats[16 + pass], (unsigned long long)dbg_iters);
+#endif
         // bit position = the caller's sample index
         const int bit = s_perm[ii];
         const unsigned lo_bit = (alive && bit < 32) ? (1u << bit) : 0u, hi_bit = (alive && bit >= 32) ? (1u << (bit - 32)) : 0u;
@@ -764,6 +776,14 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                 uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, nc >> 16, P.n_inner, mrq,
                                                sm.uv, sm.perm, P.S, lane, sm.u.p2.wq[tid >> 5], sm.u.p2.wk[tid >> 5], sm.u.p2.wb[tid >> 5]);
                 if (lane == 0) finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
+#ifdef DAISY_FF_STATS
+                if (lane == 0) {
+                    const int nm = nc & 0xffff, pc = __popcll(mask);
+                    const int cat = nm == 0 ? 0 : (pc == 0 ? 1 : (pc == P.S ? 2 : 3)); // simple / occluded / visible / partial
+                    atomicAdd(&g_ffstats[cat], 1ull); atomicAdd(&g_ffstats[4 + cat], (unsigned long long)nm); atomicAdd(&g_ffstats[8 + cat], (unsigned long long)(nc >> 16));
+                    if (nm == 0 && pc == P.S) atomicAdd(&g_ffstats[12], 1ull);
+                }
+#endif
             }
             __syncwarp();
         }
@@ -903,6 +923,18 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     DZ_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+#ifdef DAISY_FF_STATS
+    {
+        unsigned long long h[32];
+        cudaMemcpyFromSymbol(h, g_ffstats, sizeof(h));
+        const char *nm[4] = { "simple(n_main=0)", "occluded", "visible", "partial" };
+        for (int c = 0; c < 4; c++)
+            fprintf(stderr, "ffstats %-18s pairs %12llu  mean n_main %7.1f  mean n_ring %6.1f\n", nm[c], h[c], h[c] ? (double)h[4 + c] / h[c] : 0.0, h[c] ? (double)h[8 + c] / h[c] : 0.0);
+        fprintf(stderr, "ffstats simple&fully-visible %llu ; slab iterations pass0 %llu pass1 %llu\n", h[12], h[16], h[17]);
+        unsigned long long z[32] = { 0 };
+        cudaMemcpyToSymbol(g_ffstats, z, sizeof(z));
+    }
+#endif
     if (write_F) { ctx->ff_ms = ms; ctx->pairs_traced = (int64_t)pairs[0]; ctx->pairs_owned = (int64_t)pairs[1]; ctx->pairs_heavy = (int64_t)pairs[2]; }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_jobs); cudaFree(d_counter); cudaFree(d_pairs); cudaFree(d_scratch);
