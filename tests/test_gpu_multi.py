@@ -39,9 +39,17 @@ B, R = s.read_local()
 s.reset()
 again = [s.step(True) for _ in range(4)] # a second solve after reset() must repeat the first one
 assert np.array_equal(again[3], sums[3]) and np.array_equal(again[1], sums[1])
+# wide-band solve on the tensor-core kernel with the same partition
+K2 = 32
+M2 = rng.uniform(0, 0.06, (len(sc.materials), K2, K2)).astype(np.float32)
+E2 = (rng.uniform(0, 7, (K2, 2048)) * (rng.uniform(0, 1, (K2, 2048)) < 0.1)).astype(np.float32)
+s2 = ddist.PartitionedSolver(p, K2, E2, M2, sc.mat_idx, fused=bool(int(os.environ["DAISY_FUSED"])))
+sums2 = [s2.step(True) for _ in range(3)]
+B32, R32 = s2.read_local()
+s2.close()
 st = p.stats()
 np.savez(os.path.join(os.environ["DAISY_OUT"], f"rank{rank}.npz"), F=F, B=B, R=R, r0=r0, r1=r1, sums=np.array(sums),
-         owned=st["pairs_owned"], traced=st["pairs_traced"])
+         owned=st["pairs_owned"], traced=st["pairs_traced"], B32=B32, R32=R32, sums32=np.array(sums2))
 s.close(); p.close()
 torch.distributed.destroy_process_group()
 '''
@@ -90,5 +98,23 @@ def test_two_gpu_sharded_build_and_exchange(tmp_path, peer, fused):
     assert np.allclose(B2, B1, rtol=1e-5, atol=1e-6 * np.abs(B1).max()) and np.allclose(R2, R1, rtol=1e-5, atol=1e-6 * np.abs(R1).max())
     got = outs[0]["sums"]
     assert np.allclose(got[[0, 1, 3]], np.array(sums1)[[0, 1, 3]], rtol=1e-6) and np.array_equal(outs[0]["sums"], outs[1]["sums"])
+    L.daisy_solver_destroy(s)
+    # K = 32 (tcgen05 kernel): partitioned == single GPU within 1e-5
+    K2 = 32
+    M2 = rng.uniform(0, 0.06, (len(sc.materials), K2, K2)).astype(np.float32)
+    E2 = (rng.uniform(0, 7, (K2, 2048)) * (rng.uniform(0, 1, (K2, 2048)) < 0.1)).astype(np.float32)
+    s = C.c_void_p()
+    _lib.check(L.daisy_solver_create(p._ctx, K2, _lib.fptr(E2), _lib.fptr(M2), M2.shape[0], _lib.iptr(sc.mat_idx), C.byref(s)))
+    sums32 = []
+    for _ in range(3):
+        t = np.zeros(K2)
+        _lib.check(L.daisy_solver_step(s, t.ctypes.data_as(C.POINTER(C.c_double))))
+        sums32.append(t)
+    B1, R1 = np.empty_like(E2), np.empty_like(E2)
+    _lib.check(L.daisy_solver_read(s, _lib.fptr(B1), _lib.fptr(R1)))
+    B2 = np.concatenate([o["B32"] for o in outs], axis=1)
+    R2 = np.concatenate([o["R32"] for o in outs], axis=1)
+    assert np.allclose(B2, B1, rtol=1e-5, atol=1e-6 * np.abs(B1).max()) and np.allclose(R2, R1, rtol=1e-5, atol=1e-6 * np.abs(R1).max())
+    assert np.allclose(outs[0]["sums32"], np.array(sums32), rtol=2e-6) and np.array_equal(outs[0]["sums32"], outs[1]["sums32"])
     L.daisy_solver_destroy(s)
     p.close()
