@@ -7,7 +7,9 @@
 // The reference materialises N^2 16-byte triplets on the host, generates 24-byte rays on one CPU thread, ships
 // them to OptiX Prime in 4M-ray batches and reduces 16-byte hits on the host.  Here one kernel owns a 64x64 tile
 // of the upper triangle: it evaluates the 16 sub-patch terms once (they serve F(r,c) and F(c,r)), generates the
-// rays in registers, walks the LBVH, and writes both mirrored tiles coalesced through shared memory.
+// rays in registers, resolves them against per-pair candidate lists (shaft walk of the LBVH; triangles coplanar with
+// one of the two patches are only tested by the few samples near the patch edges, see k_tri_planes) and writes both
+// mirrored tiles coalesced through shared memory -- into this rank's matrix or a peer's over NVLink.
 #include "daisy_common.cuh"
 #include <math.h>
 #include <stdlib.h>

@@ -6,12 +6,15 @@
 //   BWLightning::increment_lightpass                :419-424  (K=1, M = [1])
 //   converge_lightning / check_convergence          :145-151, :255-261, :336-340, :410-415
 //
-// F is dense FP32, row-major, resident in HBM; one pass streams it exactly once.  k_gather_partial is a persistent
-// kernel: a work item is (64-row block) x (column range); a warp owns R rows, lanes stride the columns with 128-bit
-// streaming loads, the K residual bands of the current 512-column tile are staged in shared memory by 1-D TMA bulk
-// copies (cp.async.bulk + mbarrier, double buffered) and every F element is used for K FMAs straight from
-// registers.  k_gather_epilogue sums the column-range partials, applies the per-material KxK matrix, accumulates
-// B, writes the new residual into the exchange block of this rank and totals the per-band residual sums.
+// F is dense FP32, row-major, resident in HBM; one pass streams it exactly once.  Three main kernels, all persistent
+// with work items (row block) x (column range):
+//   k_gather_tma<K>      K <= 9: a producer warp fills a 6-stage shared-memory ring with tiled TMA loads (F tile +
+//                        residual band slices), 8 consumer warps do K FMAs per F element; the default
+//   k_gather_mma<K>      K = 16 / 32: tcgen05 3xTF32 tensor-core kernel with the F operand staged in TMEM (gather_mma.cuh)
+//   k_gather_partial<K>  the first-generation register-prefetch kernel, kept selectable (DAISY_GATHER=ldg) as a reference point
+// k_gather_epilogue sums the column-range partials, applies the per-material KxK matrix, accumulates B, writes the new
+// residual into this rank's exchange block -- or, with the fused exchange, into every rank's buffer over NVLink -- and
+// totals the per-band residual sums.
 #include "daisy_common.cuh"
 #include <cuda.h>
 #include <math.h>
