@@ -469,8 +469,17 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         // slot is spent on them only when many lanes have one pending, not whenever a single lane does.
         int qlen = 0;
         auto flush = [&]() {
+#ifdef DAISY_FF_STATS
+            {
+                const int T = __reduce_add_sync(0xffffffffu, alive ? qlen : 0);
+                if (lane == 0 && T) { atomicAdd(&g_ffstats[20], (unsigned long long)((T + 31) / 32)); atomicAdd(&g_ffstats[21], (unsigned long long)T); }
+            }
+#endif
             for (int t = 0; t < FF_QCAP; t++) {
                 if (!__any_sync(0xffffffffu, alive && t < qlen)) break;
+#ifdef DAISY_FF_STATS
+                if (lane == 0) atomicAdd(&g_ffstats[22], 1ull);
+#endif
                 if (alive && t < qlen) {
                     const int k = wq[t * 32 + lane];
                     TriVerts tr = tv[k];
@@ -933,6 +942,8 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
         for (int c = 0; c < 4; c++)
             fprintf(stderr, "ffstats %-18s pairs %12llu  mean n_main %7.1f  mean n_ring %6.1f\n", nm[c], h[c], h[c] ? (double)h[4 + c] / h[c] : 0.0, h[c] ? (double)h[8 + c] / h[c] : 0.0);
         fprintf(stderr, "ffstats simple&fully-visible %llu ; slab iterations pass0 %llu pass1 %llu\n", h[12], h[16], h[17]);
+        fprintf(stderr, "ffstats flush: rounds executed %llu, rounds if balanced over lanes %llu, tests queued %llu (%.1f lanes per executed round)\n",
+                h[22], h[20], h[21], h[22] ? (double)h[21] / h[22] : 0.0);
         unsigned long long z[32] = { 0 };
         cudaMemcpyToSymbol(g_ffstats, z, sizeof(z));
     }
