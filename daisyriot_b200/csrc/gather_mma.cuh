@@ -17,7 +17,9 @@
 //   warps 4-11  converters (two sets alternating stages): LDS their row of the F tile, Fh = tf32(F) (round to nearest),
 //               Fl = F - Fh, tcgen05.st both into a TMEM operand ring -- the A operand is read from TMEM, so the F
 //               bytes cross shared memory exactly once on the way in and once to registers
-//   warp 1      MMA issuer: per 8-column k-step  D[:, 0:2K] += Fh x [Rh;Rl]^T  and  D[:, 0:K] += Fl x Rh^T
+//   warp 1      MMA issuer (one elected lane): per 8-column k-step  D[:, 0:2K] += Fh x [Rh;Rl]^T  and  D[:, 0:K] += Fl x Rh^T,
+//               one tcgen05.commit per stage on the mma_done ring (frees the smem slot and the operand slot, signals the
+//               epilogue); this thread is the kernel's critical path
 //   warps 12-15 epilogue: per stage tcgen05.ld the 2K accumulator columns, acc[k] += D[:, k] + D[:, K+k]; at the end
 //               of the item the column-range partials go to global memory
 //   warp 2      TMEM allocation
@@ -137,14 +139,14 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     const uint32_t raw = smem_u32(mm_smem_raw);
     unsigned char *base = mm_smem_raw + (((raw + 1023u) & ~1023u) - raw); // SWIZZLE_128B tiles need 1024-byte alignment
     uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)MM_NS * STAGE);
-    uint64_t *full = bars, *empty = bars + MM_NS, *a_full = bars + 2 * MM_NS, *a_empty = a_full + MM_NA;
-    uint64_t *mma_done = a_empty + MM_NA, *d_empty = mma_done + MM_NS; // a_empty is unused (mma_done serves it)
+    uint64_t *full = bars, *empty = bars + MM_NS, *a_full = bars + 2 * MM_NS;
+    uint64_t *mma_done = a_full + MM_NA, *d_empty = mma_done + MM_NS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_empty + MM_ND);
     static_assert(MM_NS == 4 && MM_NA == 2 && MM_ND == 4, "mma_done ring indexing below assumes these depths");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < MM_NS; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 4); mbar_init(&mma_done[i], 1); }  // empty: 4 converter warps
-        for (int i = 0; i < MM_NA; i++) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MM_NA; i++) mbar_init(&a_full[i], 4);
         for (int i = 0; i < MM_ND; i++) mbar_init(&d_empty[i], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
