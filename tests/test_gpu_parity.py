@@ -429,3 +429,33 @@ def test_sample_counts_and_inner_edge_splits_vs_bruteforce(dz, cornell512, S, ki
     assert np.array_equal(masks, masks_ref)
     assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
     p.close()
+
+
+@pytest.mark.parametrize("mode,K", [("fp32", 32), ("fp32", 12), ("ldg", 9)])
+def test_gather_alternative_kernels_vs_oracle(dz, cornell2048, uv50, monkeypatch, mode, K):
+    """The kernels behind DAISY_GATHER (CUDA-core TMA kernel for wide band counts, first-generation register-prefetch
+    kernel) stay selectable as reference points; they must meet the same 1e-5 bar."""
+    from daisyriot_b200 import _lib
+    from oracle import pyoracle
+    monkeypatch.setenv("DAISY_GATHER", mode)
+    sc = cornell2048
+    p = _ctx(dz, sc, uv50)
+    N = sc.numtriangles
+    rng = np.random.RandomState(40 + K)
+    F = (rng.uniform(0, 1, (N, N)) * (rng.uniform(0, 1, (N, N)) < 0.3) / N).astype(np.float32)
+    p.loadRadiosityMatrix(F)
+    M = rng.uniform(0, 0.3, (len(sc.materials), K, K)).astype(np.float32)
+    E = np.ascontiguousarray(rng.uniform(0, 3, (K, N)).astype(np.float32))
+    s = _solver(dz, p, K, E, M, sc.mat_idx)
+    L = _lib.lib()
+    res, B = E.copy(), E.copy()
+    for it in range(2):
+        sums = np.zeros(K)
+        _lib.check(L.daisy_solver_step(s, sums.ctypes.data_as(C.POINTER(C.c_double))))
+        sums_ref = pyoracle.gather_pass(F, res, B, M, sc.mat_idx, accum=1)
+        Bg, Rg = np.empty_like(E), np.empty_like(E)
+        _lib.check(L.daisy_solver_read(s, _lib.fptr(Bg), _lib.fptr(Rg)))
+        assert np.allclose(Rg, res, rtol=1e-5, atol=1e-5 * np.abs(res).max())
+        assert np.allclose(sums, sums_ref, rtol=1e-6)
+    L.daisy_solver_destroy(s)
+    p.close()
