@@ -47,6 +47,69 @@ protected:
         if (cuda_on) optixP.cudaCalculateRadiosityMatrix(RadMat, mesh);
         else optixP.calculateRadiosityMatrix(RadMat, mesh);
     }
+    // On-disk cache of the matrix, byte-compatible with the reference (Lightning.h:21-73): five ints (rows, cols, nnz,
+    // outerSize, innerSize), then the CSC value array, the outer index array (outerSize ints) and the inner index array.
+    // (The reference's reader takes the 4th/5th int in swapped roles; the matrix is square, so both are N.)
+    void SerializeMat(SpMat &m, char *matfile) {
+        m.makeCompressed();
+        std::ofstream f(matfile, std::ios::binary);
+        if (!f.is_open()) return;
+        const int hdr[5] = { (int)m.rows(), (int)m.cols(), (int)m.nonZeros(), (int)m.outerSize(), (int)m.innerSize() };
+        f.write((const char *)hdr, sizeof(hdr));
+        f.write((const char *)m.valuePtr(), sizeof(float) * (size_t)m.nonZeros());
+        f.write((const char *)m.outerIndexPtr(), sizeof(int) * (size_t)m.outerSize());
+        f.write((const char *)m.innerIndexPtr(), sizeof(int) * (size_t)m.nonZeros());
+    }
+    bool DeserializeMat(SpMat &m, char *matfile) {
+        std::ifstream f(matfile, std::ios::binary);
+        if (!f.is_open()) return false;
+        int hdr[5];
+        f.read((char *)hdr, sizeof(hdr));
+        const int rows = hdr[0], cols = hdr[1], nnz = hdr[2], outer = hdr[3];
+        std::vector<float> val((size_t)nnz);
+        std::vector<int> op((size_t)outer + 1), ip((size_t)nnz);
+        f.read((char *)val.data(), sizeof(float) * (size_t)nnz);
+        f.read((char *)op.data(), sizeof(int) * (size_t)outer);
+        f.read((char *)ip.data(), sizeof(int) * (size_t)nnz);
+        if (!f) return false;
+        op[outer] = nnz; // the file holds outerSize entries, i.e. no closing sentinel
+        m.resize(rows, cols);
+        m.makeCompressed();
+        m.resizeNonZeros(nnz);
+        std::copy(val.begin(), val.end(), m.valuePtr());
+        std::copy(ip.begin(), ip.end(), m.innerIndexPtr());
+        std::copy(op.begin(), op.end(), m.outerIndexPtr());
+        return true;
+    }
+    // dense rows of the cached matrix go to the GPU in chunks (daisy_formfactors_write_rows = the cache path of the C-ABI)
+    void upload(SpMat &m, OptixPrimeFunctionality &optixP) {
+        const int n = (int)m.rows();
+        Eigen::SparseMatrix<float, Eigen::RowMajor> R = m;
+        const int chunk = std::max(1, std::min(n, (int)((64u << 20) / (4u * (unsigned)std::max(n, 1)))));
+        std::vector<float> rows((size_t)chunk * n);
+        for (int r0 = 0; r0 < n; r0 += chunk) {
+            const int nr = std::min(chunk, n - r0);
+            std::fill(rows.begin(), rows.begin() + (size_t)nr * n, 0.f);
+            for (int r = 0; r < nr; r++)
+                for (Eigen::SparseMatrix<float, Eigen::RowMajor>::InnerIterator it(R, r0 + r); it; ++it) rows[(size_t)r * n + it.col()] = it.value();
+            if (!check(daisy_formfactors_write_rows(optixP.ctx, r0, nr, rows.data()))) return;
+        }
+    }
+    void initMatFromFile(MeshS &mesh, OptixPrimeFunctionality &optixP, char *matfile) { // Lightning.h:84-96
+        RadMat = SpMat(mesh.numtriangles, mesh.numtriangles);
+        if (DeserializeMat(RadMat, matfile)) {
+            upload(RadMat, optixP);
+            std::cout << "Deserialized matrix" << std::endl;
+        } else {
+            initMat(mesh, optixP);
+            SerializeMat(RadMat, matfile);
+            std::cout << "Loaded & Serialized matrix" << std::endl;
+        }
+    }
+    void initMatMaybeCached(MeshS &mesh, OptixPrimeFunctionality &optixP, char *matfile) {
+        if (matfile) initMatFromFile(mesh, optixP, matfile); // the reference's main() always takes this path (main.cpp:108)
+        else initMat(mesh, optixP);
+    }
     void create(MeshS &mesh, OptixPrimeFunctionality &optixP, int K_, const std::vector<float> &E, const std::vector<float> &M) {
         K = K_; N = mesh.numtriangles;
         check(daisy_solver_create(optixP.ctx, K, E.data(), M.data(), (int)mesh.materials.size(), mesh.materialIndexPerTriangle.data(), &solver));
@@ -82,7 +145,7 @@ public:
             }
         for (int m = 0; m < nm; m++) // set_reflectionmatrix, :287-292 (one matrix per material instead of per patch)
             std::copy(mesh.materials[m].M.data(), mesh.materials[m].M.data() + Kw * Kw, M.begin() + (size_t)m * Kw * Kw);
-        initMat(mesh, optixP);
+        initMatMaybeCached(mesh, optixP, matfile);
         create(mesh, optixP, Kw, E, M);
         reset();
         std::cout << "Lightning has been initialized" << std::endl;
@@ -115,7 +178,7 @@ public:
         for (int m = 0; m < nm; m++)
             for (int i = 0; i < 3; i++)
                 if (mesh.materials[m].rgbcolor[i] > 0.0) M[(size_t)m * 9 + i * 3 + i] = mesh.materials[m].rgbcolor[i];
-        initMat(mesh, optixP);
+        initMatMaybeCached(mesh, optixP, matfile);
         create(mesh, optixP, 3, E, M);
         reset();
         converge_lightning();
@@ -133,7 +196,7 @@ public:
             float e = mesh.materials[mesh.materialIndexPerTriangle[j]].emission[0];
             if (e > 0.0) E[j] = e * emission_value;
         }
-        initMat(mesh, optixP);
+        initMatMaybeCached(mesh, optixP, matfile);
         create(mesh, optixP, 1, E, M);
         reset();
         converge_lightning();

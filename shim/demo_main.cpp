@@ -1,6 +1,6 @@
 // demo_main.cpp -- the reference's start-up sequence (main.cpp:94-108) without the window: load the scene with the
 // reference's own MeshS/Material code, build form factors and converge the lighting through the shim classes.
-//   shim_demo <scene.obj> <mtl_dir/> <method 0|1|2> <emission_value> <seed> [rands.bin]   (cwd must hold color_tables/srgb.coeff)
+//   shim_demo <scene.obj> <mtl_dir/> <method 0|1|2> <emission_value> <seed> [rands.bin] [matrix cache file]   (cwd must hold color_tables/srgb.coeff)
 // Prints one line of results the parity test compares with the Python path.
 #include <cstdio>
 #include <vector>
@@ -26,7 +26,7 @@ int main(int argc, char **argv) {
     }
     float emission = (float)atof(argv[4]);
     int method = atoi(argv[3]);
-    Lightning *l = Lightning::get_lightning(method, mesh, optixP, emission, wavelengths, true, nullptr);
+    Lightning *l = Lightning::get_lightning(method, mesh, optixP, emission, wavelengths, true, argc > 7 ? argv[7] : nullptr); // main.cpp:108 passes matfile
     double sum = 0;
     for (auto &band : l->lightningvalues) for (float v : band) sum += v;
     glm::vec3 c = l->get_color_of_patch(mesh.numtriangles / 2);

@@ -40,3 +40,32 @@ def test_cpp_shim_matches_python_mirror(tmp_path, coeff_model, uv50, method):
     c = lt.get_color_of_patch(sc.numtriangles // 2)
     assert np.allclose([float(m.group(i)) for i in (3, 4, 5)], c, rtol=1e-4, atol=1e-5)
     lt.close(); p.close()
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO), reason="shim demo is built where /root/reference exists (make -C shim)")
+def test_cpp_shim_matrix_cache_roundtrip(tmp_path, coeff_model, uv50):
+    """initMatFromFile (reference Lightning.h:84-96; main.cpp:108 always passes a matfile): the first run builds the matrix
+    and writes the cache in the reference's byte layout, the second run loads it instead of tracing -- same result; and the
+    file the C++ side wrote is what the Python mirror reads and what the GPU matrix converts to."""
+    import daisyriot_b200 as dz
+    from daisyriot_b200 import api, scenes
+    model, cwd = coeff_model
+    sc = scenes.cornell_box(1024)
+    obj, _ = scenes.write_obj(sc, cwd, "shim_cache_scene")
+    rands = os.path.join(cwd, "rands_cache.bin")
+    uv50.astype(np.float32).tofile(rands)
+    matfile = str(tmp_path / "radmat.bin")
+    outs = []
+    for run in range(2):
+        out = subprocess.run([DEMO, obj, cwd + "/", "2", "7.0", "1", rands, matfile], cwd=cwd, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert ("Loaded & Serialized matrix" if run == 0 else "Deserialized matrix") in out.stdout
+        outs.append(re.search(r"RESULT (passes=\d+ sumB=\S+ color=\S+)", out.stdout).group(1))
+    assert outs[0] == outs[1]
+    # the file against the Python mirror
+    F_file = api.deserialize_mat(matfile)
+    wl = np.arange(200, 601, 50).astype(np.float32)
+    p = dz.OptixPrimeFunctionality(dz.MeshS.from_scene(sc, wl, model), rands=uv50)
+    F_gpu = p.cudaCalculateRadiosityMatrix().rows()
+    assert np.array_equal(np.asarray(F_file, np.float32).view(np.uint32), F_gpu.view(np.uint32))
+    p.close()
