@@ -98,6 +98,26 @@ public:
         return visibility / rands.size();
     }
 
+    // .cpp:169-242 -- every pair row < col of the triplet list with a positive unoccluded factor is traced with the sample
+    // pattern; pairs with visibility > 0 yield (row, col, vis * ff(row,col)) and (col, row, vis * ff(col,row)).  The reference
+    // signature also takes the OptiX context and model; here the fused GPU kernel does list, rays and reduction in one go, so
+    // the unoccluded list and the pattern arguments are implied by the context (same values by construction).  The order of the
+    // returned triplets is column-major instead of the reference's push order; setFromTriplets does not depend on it.
+    std::vector<Eigen::Triplet<double>> calculateAllVisibility(std::vector<parallellism::Tripl> & /*tripletlist*/, MeshS &mesh,
+                                                               std::vector<UV> & /*rands*/) {
+        std::vector<Eigen::Triplet<double>> out;
+        if (!report(daisy_formfactors_build(ctx, DAISY_FF_DEVICE))) return out;
+        int64_t nnz = 0;
+        if (!report(daisy_formfactors_to_csc(ctx, &nnz, nullptr, nullptr, nullptr))) return out;
+        std::vector<float> val((size_t)nnz);
+        std::vector<int> inner((size_t)nnz), outer((size_t)mesh.numtriangles + 1);
+        if (!report(daisy_formfactors_to_csc(ctx, &nnz, val.data(), inner.data(), outer.data()))) return out;
+        out.reserve((size_t)nnz);
+        for (int c = 0; c < mesh.numtriangles; c++)
+            for (int i = outer[c]; i < outer[c + 1]; i++) out.emplace_back(inner[i], c, (double)val[i]);
+        return out;
+    }
+
     // .cpp:133-167 (unoccluded 4x4 rule times visibility, host arithmetic)
     float p2pFormfactor(int originPatch, int destPatch, MeshS &mesh) {
         daisy_tripl t;

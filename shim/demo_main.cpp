@@ -30,7 +30,13 @@ int main(int argc, char **argv) {
     double sum = 0;
     for (auto &band : l->lightningvalues) for (float v : band) sum += v;
     glm::vec3 c = l->get_color_of_patch(mesh.numtriangles / 2);
-    printf("RESULT passes=%d sumB=%.9e color=%.6f,%.6f,%.6f rand0=%.9g\n", l->numpasses, sum, c.x, c.y, c.z, optixP.rands[0].u);
+    // the batched visibility entry point on its own (OptixPrimeFunctionality.cpp:169-242): count and sum of the triplets
+    std::vector<parallellism::Tripl> unoccluded;
+    std::vector<Eigen::Triplet<double>> tr = optixP.calculateAllVisibility(unoccluded, mesh, optixP.rands);
+    double tsum = 0;
+    for (auto &t : tr) tsum += t.value();
+    printf("RESULT passes=%d sumB=%.9e color=%.6f,%.6f,%.6f rand0=%.9g tripl=%zu,%.12e\n", l->numpasses, sum, c.x, c.y, c.z, optixP.rands[0].u,
+           tr.size(), tsum);
     delete l;
     return 0;
 }

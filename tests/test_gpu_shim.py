@@ -68,4 +68,8 @@ def test_cpp_shim_matrix_cache_roundtrip(tmp_path, coeff_model, uv50):
     p = dz.OptixPrimeFunctionality(dz.MeshS.from_scene(sc, wl, model), rands=uv50)
     F_gpu = p.cudaCalculateRadiosityMatrix().rows()
     assert np.array_equal(np.asarray(F_file, np.float32).view(np.uint32), F_gpu.view(np.uint32))
+    # calculateAllVisibility through the shim: one triplet per non-zero entry, same total
+    m = re.search(r"tripl=(\d+),(\S+)", out.stdout)
+    assert int(m.group(1)) == int(np.count_nonzero(F_gpu))
+    assert abs(float(m.group(2)) - F_gpu.astype(np.float64).sum()) <= 1e-9 * F_gpu.astype(np.float64).sum()
     p.close()
