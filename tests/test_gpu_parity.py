@@ -459,3 +459,62 @@ def test_gather_alternative_kernels_vs_oracle(dz, cornell2048, uv50, monkeypatch
         assert np.allclose(sums, sums_ref, rtol=1e-6)
     L.daisy_solver_destroy(s)
     p.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_irregular_walls_vs_bruteforce(dz, uv50, seed):
+    """Adversarial input for coplanar skipping: two facing walls and a tilted occluder triangulated irregularly (jittered grids,
+    random diagonals, slivers, triangles 20x larger than their neighbours), vertex heights perturbed by rounding-sized noise
+    on part of each wall, arbitrary wall orientation.  Masks and matrix must equal the brute-force oracle bit for bit."""
+    from daisyriot_b200.scenes import Scene
+    rng = np.random.RandomState(seed)
+
+    def rot(axis, ang):
+        axis = axis / np.linalg.norm(axis)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+    R = rot(rng.normal(size=3), rng.uniform(0, 3))
+    V, T, VN = [], [], []
+
+    def wall(origin, eu, ev, n, nu, nv, flip):
+        base = len(V)
+        us = np.sort(np.concatenate([[0, 1], rng.uniform(0, 1, nu - 1)]))
+        vs = np.sort(np.concatenate([[0, 1], rng.uniform(0, 1, nv - 1)]))
+        if seed == 2:
+            us[1] = us[0] + 1e-3  # a column of slivers
+        for j in range(nv + 1):
+            for i in range(nu + 1):
+                p = origin + us[i] * eu + vs[j] * ev
+                if rng.uniform() < 0.3:
+                    p = p + n * rng.uniform(-2e-7, 2e-7) * 6.0
+                V.append(p)
+        ni = len(VN)
+        VN.append(n)
+        for j in range(nv):
+            for i in range(nu):
+                a, b, c, d = base + j * (nu + 1) + i, base + j * (nu + 1) + i + 1, base + (j + 1) * (nu + 1) + i, base + (j + 1) * (nu + 1) + i + 1
+                tris = [(a, b, d), (a, d, c)] if rng.uniform() < 0.5 else [(a, b, c), (b, d, c)]
+                for t in tris:
+                    T.append([*(t[::-1] if flip else t), ni, ni, ni])
+
+    ex, ey, ez = np.eye(3)
+    wall(np.zeros(3), 6 * ex, 6 * ez, ey, 9, 8, True)                       # floor, facing +y
+    wall(np.array([0, 4.0, 0]), 6 * ex, 6 * ez, -ey, 7, 9, False)           # ceiling, facing -y
+    wall(np.array([1.5, 1.7, 1.0]), 2.5 * ex + 0.4 * ey, 3 * ez, np.cross(2.5 * ex + 0.4 * ey, 3 * ez) / np.linalg.norm(np.cross(2.5 * ex + 0.4 * ey, 3 * ez)), 4, 5, False)
+    big = len(V)                                                            # one triangle much larger than its neighbours
+    V += [np.array([6.0, 0, 0]), np.array([9.0, 0, 0]), np.array([6.0, 0, 6.0])]
+    T.append([big, big + 2, big + 1, 0, 0, 0])
+    V = (np.asarray(V) @ R.T).astype(np.float32)
+    VN = (np.asarray(VN) @ R.T).astype(np.float32)
+    T = np.asarray(T, np.int32)
+    mats = [{"name": "w", "Kd": np.ones(3, np.float32), "Ke": np.zeros(3, np.float32), "Ks": np.zeros(3, np.float32)}]
+    sc = Scene(V, VN, T, np.zeros(len(T), np.int32), mats, f"irregular{seed}")
+    p = _ctx(dz, sc, uv50)
+    F = p.cudaCalculateRadiosityMatrix().rows()
+    masks = p.visibilityMasks()
+    F_ref, masks_ref, _ = _oracle(sc).radmat_rows(uv50, 0, sc.numtriangles, brute=True)
+    assert (masks_ref != 0).sum() > 1000  # the walls do see each other
+    assert np.array_equal(masks, masks_ref)
+    assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
+    p.close()
