@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <unordered_map>
 #include <vector>
 
 static thread_local char g_err[1024] = "";
@@ -29,7 +30,7 @@ static void free_ctx(daisy_ctx *c) {
     if (c->peers_set)
         for (int g = 0; g < c->nranks && g < 16; g++)
             if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
-    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane);
+    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane); cudaFree(c->d_pid);
     cudaFree(c->d_nodes); cudaFree(c->d_F);
     delete c;
 }
@@ -90,6 +91,29 @@ extern "C" int daisy_ctx_create(const float *vertices, int nv, const float *norm
     if (nv) CC(cudaMemcpy(c->d_vertices, vertices, sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice));
     if (nn) CC(cudaMemcpy(c->d_normals, normals, sizeof(float) * 3 * (size_t)nn, cudaMemcpyHostToDevice));
     if (ntri) CC(cudaMemcpy(c->d_tri, tri_idx, sizeof(int) * 6 * (size_t)ntri, cudaMemcpyHostToDevice));
+    {
+        // exact axis-aligned plane ids: triangles whose three vertices carry the very same x (or y, or z) share an id.  Lets the
+        // form-factor kernel recognise "coplanar with this patch" for walls, floors and the like by an integer compare.
+        std::vector<int> pid((size_t)(ntri > 0 ? ntri : 1), 0);
+        std::unordered_map<uint64_t, int> ids;
+        for (int i = 0; i < ntri; i++) {
+            const float *a = vertices + 3 * (size_t)tri_idx[6 * (size_t)i], *b = vertices + 3 * (size_t)tri_idx[6 * (size_t)i + 1],
+                        *cc = vertices + 3 * (size_t)tri_idx[6 * (size_t)i + 2];
+            int axis = -1, count = 0;
+            for (int d = 0; d < 3; d++)
+                if (a[d] == b[d] && a[d] == cc[d]) { axis = d; count++; }
+            if (count != 1) continue; // not axis-aligned, or degenerate (a segment or a point)
+            float v = a[axis] + 0.0f; // -0 -> +0
+            uint32_t bits;
+            memcpy(&bits, &v, 4);
+            const uint64_t key = ((uint64_t)axis << 32) | bits;
+            auto it = ids.find(key);
+            if (it == ids.end()) it = ids.emplace(key, (int)ids.size() + 1).first;
+            pid[(size_t)i] = it->second;
+        }
+        CC(cudaMalloc(&c->d_pid, sizeof(int) * pid.size()));
+        CC(cudaMemcpy(c->d_pid, pid.data(), sizeof(int) * pid.size(), cudaMemcpyHostToDevice));
+    }
 #undef CC
     int rc = dz_build_lbvh(c);
     if (!rc) rc = dz_precompute_geom(c);

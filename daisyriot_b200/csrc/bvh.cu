@@ -161,7 +161,7 @@ __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__res
 }
 
 __global__ void k_pack_nodes(const uint64_t *__restrict__ keys, int N, const int2 *__restrict__ children,
-                             const float *__restrict__ box, BvhNode *__restrict__ nodes) {
+                             const float *__restrict__ box, const int *__restrict__ pid, BvhNode *__restrict__ nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N - 1) return;
     int2 ch = children[i];
@@ -175,7 +175,7 @@ __global__ void k_pack_nodes(const uint64_t *__restrict__ keys, int N, const int
     // leaves refer to the ORIGINAL triangle id
     int li = ch.x >= 0 ? ch.x : ~(int)(uint32_t)keys[~ch.x];
     int ri = ch.y >= 0 ? ch.y : ~(int)(uint32_t)keys[~ch.y];
-    n.d = make_int4(li, ri, 0, 0);
+    n.d = make_int4(li, ri, li < 0 ? pid[~li] : 0, ri < 0 ? pid[~ri] : 0);
     nodes[i] = n;
 }
 
@@ -213,7 +213,7 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     }
     k_refit<<<(N + 255) / 256, 256, 0, st>>>(d_keys, ctx->d_triverts, N, ctx->pad, d_children, d_parent, d_box, d_flags, ctx->d_tribox);
     if (N > 1) {
-        k_pack_nodes<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_box, ctx->d_nodes);
+        k_pack_nodes<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_box, ctx->d_pid, ctx->d_nodes);
         ctx->root = 0;
     } else {
         ctx->root = ~0; // single triangle: the root is the leaf of triangle 0

@@ -165,7 +165,7 @@ struct __align__(16) BvhNode {
     float4 a; // L.lo.x L.lo.y L.lo.z L.hi.x
     float4 b; // L.hi.y L.hi.z R.lo.x R.lo.y
     float4 c; // R.lo.z R.hi.x R.hi.y R.hi.z
-    int4 d;   // left, right, 0, 0
+    int4 d;   // left, right, plane id of the left child if it is a leaf (else 0), same for the right child
 };
 
 // conservative slab test against [0, tmax]; boxes are padded at build time, fminf/fmaxf drop the NaN of 0*inf
@@ -213,6 +213,7 @@ struct daisy_ctx {
     TriVerts *d_triverts = nullptr;
     float4 *d_tribox = nullptr; // padded per-triangle boxes (2 float4 each), same boxes as the LBVH leaves
     PatchGeom *d_geom = nullptr;
+    int *d_pid = nullptr;       // per triangle: id (>= 1) of the axis-aligned plane all three vertices lie in EXACTLY, 0 if none
     float4 *d_plane = nullptr;  // per triangle: unit geometric normal, w = smallest altitude if coplanar skipping is safe for it, else -1
     float ext = 0.f;            // largest scene extent
     // LBVH

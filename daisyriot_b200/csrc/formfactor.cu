@@ -378,7 +378,7 @@ __device__ __forceinline__ bool shaft_box(const Shaft &s, float lox, float loy, 
 
 // Premise of coplanar skipping for one side of a pair (see k_tri_planes): unit normal n and a point a of the patch's
 // plane; on = the patch qualifies and every ray of the pair meets the plane steeply enough.
-struct RingSide { float nx, ny, nz, ax, ay, az; bool on; };
+struct RingSide { float nx, ny, nz, ax, ay, az; bool on; int pid; }; // pid: exact axis-aligned plane id of the patch (0 = none)
 
 // true if all three vertices of T lie within tau of the plane (n, a)
 __device__ __forceinline__ bool tri_in_plane(const RingSide &r, const TriVerts &T, float tau) {
@@ -405,12 +405,14 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
     int sp = 0;
     int cur = root;
     bool overflow = false;
-    auto leaf = [&](int k, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    auto leaf = [&](int k, int kp, float lox, float loy, float loz, float hix, float hiy, float hiz) {
         if (k == lo || k == hi) return;
         if (n_main + n_ring == SHAFT_CAP) { overflow = true; return; }
-        bool ring = false;
-        const bool tl = rl.on && box_meets_plane(rl, lox, loy, loz, hix, hiy, hiz);
-        const bool th = rh.on && box_meets_plane(rh, lox, loy, loz, hix, hiy, hiz);
+        // exact plane ids decide without looking at the geometry whenever both the candidate and the patch have one:
+        // equal ids = all six vertices share one coordinate exactly; different ids = different axis-aligned planes
+        bool ring = (rl.on && kp != 0 && kp == rl.pid) || (rh.on && kp != 0 && kp == rh.pid);
+        const bool tl = !ring && rl.on && (kp == 0 || rl.pid == 0) && box_meets_plane(rl, lox, loy, loz, hix, hiy, hiz);
+        const bool th = !ring && rh.on && (kp == 0 || rh.pid == 0) && box_meets_plane(rh, lox, loy, loz, hix, hiy, hiz);
         if (tl || th) {
             const TriVerts T = tv[k];
             ring = (tl && tri_in_plane(rl, T, tau)) || (th && tri_in_plane(rh, T, tau));
@@ -423,8 +425,8 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
         BvhNode nd = nodes[cur];
         bool hl = shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
         bool hr = shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
-        if (hl && nd.d.x < 0) { leaf(~nd.d.x, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y); hl = false; }
-        if (hr && nd.d.y < 0) { leaf(~nd.d.y, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w); hr = false; }
+        if (hl && nd.d.x < 0) { leaf(~nd.d.x, nd.d.z, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y); hl = false; }
+        if (hr && nd.d.y < 0) { leaf(~nd.d.y, nd.d.w, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w); hr = false; }
         if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
         else if (hl) cur = nd.d.x;
         else if (hr) cur = nd.d.y;
@@ -572,6 +574,7 @@ struct FFParams {
     const BvhNode *nodes;
     const float4 *tribox; // padded triangle boxes, 2 float4 per triangle
     const float4 *plane;  // per-triangle plane record (k_tri_planes)
+    const int *pid;       // per-triangle exact axis-aligned plane id (0 = none)
     float tau;            // coplanarity tolerance
     int n_inner;          // samples [0, n_inner) of the device-order pattern are inner samples
     int ring_on;          // coplanar skipping enabled
@@ -608,6 +611,7 @@ struct FFSmem {
     float area_r[TILE], area_c[TILE]; // patch areas (needed after phase 1 by the host-variant reciprocity rule)
     TriVerts tr[TILE], tc[TILE];
     float4 pr[TILE], pc[TILE]; // plane records of the row / column patches
+    int pid_r[TILE], pid_c[TILE]; // their exact plane ids
     unsigned char perm[DAISY_MAX_SAMPLES];
     float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
     float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
@@ -657,8 +661,8 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
             ((float4 *)&s_tr[p])[q] = ((const float4 *)&P.tv[gr])[q];
             ((float4 *)&s_tc[p])[q] = ((const float4 *)&P.tv[gc])[q];
         }
-        if (tid < TILE) { sm.pr[tid] = P.plane[min(R0 + tid, P.N - 1)]; sm.area_r[tid] = P.geom[min(R0 + tid, P.N - 1)].n.w; }
-        else if (tid < 2 * TILE) { sm.pc[tid - TILE] = P.plane[min(C0 + tid - TILE, P.N - 1)]; sm.area_c[tid - TILE] = P.geom[min(C0 + tid - TILE, P.N - 1)].n.w; }
+        if (tid < TILE) { sm.pr[tid] = P.plane[min(R0 + tid, P.N - 1)]; sm.area_r[tid] = P.geom[min(R0 + tid, P.N - 1)].n.w; sm.pid_r[tid] = P.pid[min(R0 + tid, P.N - 1)]; }
+        else if (tid < 2 * TILE) { sm.pc[tid - TILE] = P.plane[min(C0 + tid - TILE, P.N - 1)]; sm.area_c[tid - TILE] = P.geom[min(C0 + tid - TILE, P.N - 1)].n.w; sm.pid_c[tid - TILE] = P.pid[min(C0 + tid - TILE, P.N - 1)]; }
         __syncthreads();
 
         // ---- phase 1: unoccluded form factors of every pair r < c of the tile; facing pairs go on the list
@@ -744,6 +748,7 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                 // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
                 RingSide rl_, rh_;
                 rl_.on = rh_.on = false;
+                rl_.pid = sm.pid_r[rl]; rh_.pid = sm.pid_c[cl];
                 if (P.ring_on) {
                     const float4 pl = sm.pr[rl], ph = sm.pc[cl];
                     const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
@@ -899,7 +904,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     DZ_CUDA(cudaMemsetAsync(d_pairs, 0, 3 * sizeof(unsigned long long), st));
     FFParams P;
     P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.tribox = ctx->d_tribox; P.scratch = nullptr; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
-    P.plane = ctx->d_plane; P.tau = COPLANAR_TAU * ctx->ext; P.n_inner = ctx->n_nonedge;
+    P.plane = ctx->d_plane; P.pid = ctx->d_pid; P.tau = COPLANAR_TAU * ctx->ext; P.n_inner = ctx->n_nonedge;
     { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
