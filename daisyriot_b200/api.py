@@ -188,6 +188,62 @@ class OptixPrimeFunctionality:
         seen = np.count_nonzero((hits["t"] > 0) & (hits["triangleId"] == destPatch))
         return float(np.float32(seen) / np.float32(rays.shape[0]))
 
+    # -- float p2pFormfactor(int originPatch, int destPatch, MeshS&)     (4x4 rule, host arithmetic, x visibility)   .cpp:133-167
+    def p2pFormfactor(self, originPatch: int, destPatch: int, mesh=None) -> float:
+        row = self.runCalculateRadiosityMatrix(originPatch, 1, _lib.FF_HOST)[0]
+        return float(np.float32(row["m_value"][destPatch]) * np.float32(self.calculateVisibility(originPatch, destPatch)))
+
+    # triangle_math helpers in the reference's float32 operation order                         triangle_math.cpp:16-29, 31-35, 76-86
+    def _centre(self, tri: int) -> np.ndarray:
+        m = self.mesh
+        a, b, c = (m.vertices[m.triangleIndices[tri, k]] for k in range(3))
+        return ((a + b + c) / np.float32(3)).astype(np.float32)
+
+    def _avg_normal(self, tri: int) -> np.ndarray:
+        m = self.mesh
+        n = (m.normals[m.triangleIndices[tri, 3]] + m.normals[m.triangleIndices[tri, 4]] + m.normals[m.triangleIndices[tri, 5]]) / np.float32(3)
+        return _normalize32(n.astype(np.float32))
+
+    def _is_facing_back(self, origin: np.ndarray, destPatch: int) -> bool:
+        d = _normalize32((self._centre(destPatch) - origin).astype(np.float32))
+        return bool(_dot32(d, self._avg_normal(destPatch)) >= 0)
+
+    # -- float p2pFormfactorNusselt(int originPatch, int destPatch, MeshS&)                                  .cpp:273-306
+    def p2pFormfactorNusselt(self, originPatch: int, destPatch: int, mesh=None) -> float:
+        """Nusselt analogue: the destination triangle projected onto the unit hemisphere around the origin patch's centre
+        and then onto its plane, area / pi, times the sampled visibility.  The reference guards with
+        ``if (isFacingBack(a), isFacingBack(b))`` -- a comma expression, so only the second test counts; kept as is."""
+        m = self.mesh
+        co, cd = self._centre(originPatch), self._centre(destPatch)
+        no = self._avg_normal(originPatch)
+        if self._is_facing_back(cd, originPatch):
+            return 0.0
+        proj = []
+        for i in range(3):
+            v = m.vertices[m.triangleIndices[destPatch, i]]
+            h = (co + _normalize32((v - co).astype(np.float32))).astype(np.float32)
+            proj.append((h - _dot32(no, (h - co).astype(np.float32)) * no).astype(np.float32))
+        ab, ac = (proj[1] - proj[0]).astype(np.float32), (proj[2] - proj[0]).astype(np.float32)
+        cr = np.array([ab[1] * ac[2] - ac[1] * ab[2], ab[2] * ac[0] - ac[2] * ab[0], ab[0] * ac[1] - ac[0] * ab[1]], np.float32)
+        surface = np.float32(0.5 * float(np.sqrt(_dot32(cr, cr), dtype=np.float32)))
+        ff = np.float32(surface / np.float32(math.pi))
+        return float(np.float32(ff * np.float32(self.calculateVisibility(originPatch, destPatch))))
+
+    # -- bool shootPatchRay(vector<Hit>& patches, MeshS&)     one ray between two picked surface points              .cpp:456-469
+    def shootPatchRay(self, patches, mesh=None) -> bool:
+        m = self.mesh
+        f = np.float32
+
+        def uv2xyz(h):
+            a, b, c = (m.vertices[m.triangleIndices[int(h["triangleId"]), k]] for k in range(3))
+            return ((a + f(h["u"]) * (b - a)) + f(h["v"]) * (c - a)).astype(np.float32)
+
+        pa, pb = uv2xyz(patches[0]), uv2xyz(patches[1])
+        n = _normalize32((pb - pa).astype(np.float32))
+        ray = np.concatenate([(pa + n * f(0.000001)).astype(np.float32), n]).astype(np.float32)
+        hit = self.optixQuery(1, ray)
+        return bool(hit[0]["triangleId"] == patches[1]["triangleId"])
+
     def pair_rays(self, originPatch: int, destPatch: int) -> np.ndarray:
         """The S rays of ``.cpp:253-258`` (float32, reference operation order)."""
         m = self.mesh
@@ -214,6 +270,18 @@ class OptixPrimeFunctionality:
         _lib.check(_lib.lib().daisy_formfactors_stats(self._ctx, C.byref(p), C.byref(o), C.byref(r), C.byref(a), C.byref(b)))
         return {"pairs_traced": p.value, "pairs_owned": o.value, "rays": r.value, "lbvh_ms": a.value, "ff_ms": b.value,
                 "pairs_fallback": int(_lib.lib().daisy_formfactors_pairs_fallback(self._ctx))}
+
+
+def _dot32(a, b) -> np.float32:
+    """glm::dot on vec3 in float32: (x*x' + y*y') + z*z'."""
+    t = (np.asarray(a, np.float32) * np.asarray(b, np.float32)).astype(np.float32)
+    return np.float32(np.float32(t[0] + t[1]) + t[2])
+
+
+def _normalize32(v) -> np.ndarray:
+    """glm::normalize in float32: v * (1 / sqrt(dot(v, v)))."""
+    v = np.asarray(v, np.float32)
+    return (v * (np.float32(1.0) / np.sqrt(_dot32(v, v), dtype=np.float32))).astype(np.float32)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -3,7 +3,7 @@
 // C-ABI of include/daisy_b200.h.  Host code written against DaisyRiot keeps compiling: same class, same method
 // names and argument lists for optixQuery / cudaCalculateRadiosityMatrix / calculateRadiosityMatrix /
 // calculateVisibility / p2pFormfactor.  The OptiX Prime context/model members are gone (nothing here uses OptiX);
-// the camera/picking helpers (traceScreen, intersectMouse, shootPatchRay) are UI code outside this path.
+// the camera/picking helpers traceScreen and intersectMouse are UI code outside this path (they only need optixQuery).
 //
 // Error behaviour follows the reference: failures are printed to std::cerr and execution continues
 // (.cpp:45-53, :72-79, parallellism.cuh:21-26); the C layer underneath is strict and keeps the message.
@@ -127,9 +127,51 @@ public:
         return (float)t.m_value * calculateVisibility(originPatch, destPatch, mesh);
     }
 
+    // .cpp:273-306 -- Nusselt analogue (debug read-out of InputHandler.cpp:184): destination triangle projected onto the unit
+    // hemisphere around the origin patch's centre, then onto its plane; area / pi times the sampled visibility.  The reference
+    // guards with `if (isFacingBack(a), isFacingBack(b))`, a comma expression: only the second test counts (kept).
+    float p2pFormfactorNusselt(int originPatch, int destPatch, MeshS &mesh) {
+        glm::vec3 center_origin = centre(originPatch, mesh), center_dest = centre(destPatch, mesh);
+        glm::vec3 normal_origin = avgNormal(originPatch, mesh);
+        if (isFacingBack(center_dest, originPatch, mesh)) return 0.0f;
+        glm::vec3 proj[3];
+        for (int i = 0; i < 3; i++) {
+            glm::vec3 hemi = center_origin + glm::normalize(mesh.vertices[mesh.triangleIndices[destPatch].vertex[i]] - center_origin);
+            proj[i] = hemi - glm::dot(normal_origin, hemi - center_origin) * normal_origin;
+        }
+        float surface = 0.5 * glm::length(glm::cross(proj[1] - proj[0], proj[2] - proj[0]));
+        return (surface / M_PIf) * calculateVisibility(originPatch, destPatch, mesh);
+    }
+
+    // .cpp:456-469 -- one ray between two picked surface points: does it reach the second patch?
+    bool shootPatchRay(std::vector<optix_functionality::Hit> &patches, MeshS &mesh) {
+        UV ua = { patches[0].uv.x, patches[0].uv.y }, ub = { patches[1].uv.x, patches[1].uv.y };
+        glm::vec3 a = uv2xyz(patches[0].triangleId, ua, mesh), b = uv2xyz(patches[1].triangleId, ub, mesh);
+        glm::vec3 d = glm::normalize(b - a), o = a + d * 0.000001f;
+        std::vector<optix::float3> ray(2);
+        ray[0] = { o.x, o.y, o.z };
+        ray[1] = { d.x, d.y, d.z };
+        std::vector<optix_functionality::Hit> hit(1);
+        optixQuery(1, ray, hit);
+        return hit[0].triangleId == patches[1].triangleId;
+    }
+
     std::vector<UV> rands;
 
 private:
+    static glm::vec3 centre(int tri, MeshS &mesh) { // triangle_math.cpp:16-21
+        glm::vec3 c = mesh.vertices[mesh.triangleIndices[tri].vertex.x] + mesh.vertices[mesh.triangleIndices[tri].vertex.y] +
+                      mesh.vertices[mesh.triangleIndices[tri].vertex.z];
+        return glm::vec3(c.x / 3, c.y / 3, c.z / 3);
+    }
+    static glm::vec3 avgNormal(int tri, MeshS &mesh) { // triangle_math.cpp:23-29
+        glm::vec3 n = mesh.normals[mesh.triangleIndices[tri].normal.x] + mesh.normals[mesh.triangleIndices[tri].normal.y] +
+                      mesh.normals[mesh.triangleIndices[tri].normal.z];
+        return glm::normalize(glm::vec3(n.x / 3, n.y / 3, n.z / 3));
+    }
+    static bool isFacingBack(glm::vec3 origin, int destPatch, MeshS &mesh) { // triangle_math.cpp:76-86
+        return glm::dot(glm::normalize(centre(destPatch, mesh) - origin), avgNormal(destPatch, mesh)) >= 0;
+    }
     static glm::vec3 uv2xyz(int tri, const UV &uv, MeshS &mesh) { // triangle_math.cpp:3-9
         glm::vec3 a = mesh.vertices[mesh.triangleIndices[tri].vertex.x];
         glm::vec3 b = mesh.vertices[mesh.triangleIndices[tri].vertex.y];

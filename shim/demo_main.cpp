@@ -35,8 +35,15 @@ int main(int argc, char **argv) {
     std::vector<Eigen::Triplet<double>> tr = optixP.calculateAllVisibility(unoccluded, mesh, optixP.rands);
     double tsum = 0;
     for (auto &t : tr) tsum += t.value();
-    printf("RESULT passes=%d sumB=%.9e color=%.6f,%.6f,%.6f rand0=%.9g tripl=%zu,%.12e\n", l->numpasses, sum, c.x, c.y, c.z, optixP.rands[0].u,
-           tr.size(), tsum);
+    // the per-pair debugging entry points (InputHandler.cpp:184, OptixPrimeFunctionality.cpp:456-469) on two fixed patches
+    const int pa = 3, pb = mesh.numtriangles / 2 + 5;
+    float nus = optixP.p2pFormfactorNusselt(pa, pb, mesh), p2p = optixP.p2pFormfactor(pa, pb, mesh);
+    std::vector<optix_functionality::Hit> picks(2);
+    picks[0].t = 1; picks[0].triangleId = pa; picks[0].uv.x = 0.25f; picks[0].uv.y = 0.5f;
+    picks[1].t = 1; picks[1].triangleId = pb; picks[1].uv.x = 0.3f; picks[1].uv.y = 0.3f;
+    bool shot = optixP.shootPatchRay(picks, mesh);
+    printf("RESULT passes=%d sumB=%.9e color=%.6f,%.6f,%.6f rand0=%.9g tripl=%zu,%.12e nusselt=%.9e p2p=%.9e shoot=%d\n", l->numpasses, sum, c.x,
+           c.y, c.z, optixP.rands[0].u, tr.size(), tsum, nus, p2p, shot ? 1 : 0);
     delete l;
     return 0;
 }

@@ -518,3 +518,31 @@ def test_irregular_walls_vs_bruteforce(dz, uv50, seed):
     assert np.array_equal(masks, masks_ref)
     assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
     p.close()
+
+
+def test_per_pair_debug_entry_points_vs_oracle(dz, cornell512, uv50):
+    """p2pFormfactorNusselt / p2pFormfactor / shootPatchRay (OptixPrimeFunctionality.cpp:273-306, :133-167, :456-469): host
+    arithmetic around the GPU closest-hit query, against the same arithmetic around the oracle's closest hit."""
+    from daisyriot_b200 import api
+    sc = cornell512
+    p = _ctx(dz, sc, uv50)
+    orc = _oracle(sc)
+    rng = np.random.RandomState(9)
+    real_query = p.optixQuery
+    checked = 0
+    for _ in range(24):
+        a, b = (int(x) for x in rng.randint(0, sc.numtriangles, 2))
+        if a == b:
+            continue
+        got = (p.p2pFormfactorNusselt(a, b), p.p2pFormfactor(a, b))
+        p.optixQuery = lambda n, rays, hits=None: orc.query_closest(np.asarray(rays, np.float32).reshape(-1, 6)[:n])
+        want = (p.p2pFormfactorNusselt(a, b), p.p2pFormfactor(a, b))
+        picks = np.zeros(2, api.HIT_DTYPE)
+        picks["triangleId"] = [a, b]
+        picks["u"], picks["v"] = rng.uniform(0, 0.5, 2), rng.uniform(0, 0.5, 2)
+        shot_want = p.shootPatchRay(picks)
+        p.optixQuery = real_query
+        assert got == want and p.shootPatchRay(picks) == shot_want
+        checked += got[0] > 0
+    assert checked >= 3
+    p.close()

@@ -72,4 +72,14 @@ def test_cpp_shim_matrix_cache_roundtrip(tmp_path, coeff_model, uv50):
     m = re.search(r"tripl=(\d+),(\S+)", out.stdout)
     assert int(m.group(1)) == int(np.count_nonzero(F_gpu))
     assert abs(float(m.group(2)) - F_gpu.astype(np.float64).sum()) <= 1e-9 * F_gpu.astype(np.float64).sum()
+    # per-pair debugging entry points: C++ shim == Python mirror
+    m = re.search(r"nusselt=(\S+) p2p=(\S+) shoot=(\d)", out.stdout)
+    pa, pb = 3, sc.numtriangles // 2 + 5
+    assert np.isclose(float(m.group(1)), p.p2pFormfactorNusselt(pa, pb), rtol=2e-6, atol=1e-12)
+    assert np.isclose(float(m.group(2)), p.p2pFormfactor(pa, pb), rtol=2e-6, atol=1e-12)
+    picks = np.zeros(2, api.HIT_DTYPE)
+    picks["triangleId"] = [pa, pb]
+    picks["u"] = [0.25, 0.3]
+    picks["v"] = [0.5, 0.3]
+    assert int(m.group(3)) == int(p.shootPatchRay(picks))
     p.close()
