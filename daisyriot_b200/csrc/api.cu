@@ -38,9 +38,9 @@ static void free_ctx(daisy_ctx *c) {
 static void set_partition(daisy_ctx *c, int rank, int nranks) {
     c->rank = rank; c->nranks = nranks;
     int n = (c->N + nranks - 1) / nranks;
-    // single block: multiple of 4 (16-byte TMA alignment); several blocks: multiple of 128 so that a 128-column
+    // single block: multiple of 4 (16-byte TMA alignment); several blocks: multiple of 256 so that a 256-column
     // TMA tile of the residual never straddles two ranks' blocks
-    n = (nranks > 1) ? ((n + 127) / 128) * 128 : ((n + 3) / 4) * 4;
+    n = (nranks > 1) ? ((n + 255) / 256) * 256 : ((n + 3) / 4) * 4;
     if (n < 4) n = 4;
     c->rows_per_rank = n;
     c->row0 = (int)fmin((double)c->N, (double)rank * n);

@@ -233,19 +233,23 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gather_partial(GatherParams P)
 // 8 F rows and the K band slices, K FMAs per F element, then one arrive on the stage's "empty" mbarrier.  Up to
 // NSTAGE x (64+K) x 512 B (~219 KB for K=9) are in flight per SM without holding a single register, and there is no
 // CTA-wide barrier in the loop.
-#define T_COLS 128
+// The F tile of the K <= 9 kernel is 64 rows x 256 columns: 1 KB of every row per TMA box, three 73 KB stages.  With 64 x 128
+// tiles (512 B per row, six stages -- the first version) the same kernel reached 6.9 TB/s at 131072 columns; 1 KB segments
+// give 7.1 TB/s (DRAM page locality).  32 x 256 tiles (five stages) are as fast on one GPU but lose on row-sharded matrices,
+// where the residual tile (K x 256 per box, from L2) is a larger share of the traffic (measured on 2 GPUs: 0.371 / 0.357 /
+// 0.345 ms per pass for 32x256 / 64x128 / 64x256 at 32768 patches).
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // rows per consumer warp / consumer warps per CTA: the K accumulators of RW rows must fit the register file
-template <int K> struct TmaCfg { static constexpr int RW = 8, NCW = 8; };   // K <= 9 : 64-row tiles, 9 warps
-template <> struct TmaCfg<16> { static constexpr int RW = 4, NCW = 16; };   // 64-row tiles, 17 warps
-template <> struct TmaCfg<32> { static constexpr int RW = 4, NCW = 8; };    // 32-row tiles, 9 warps (FP32-pipe bound anyway)
+template <int K> struct TmaCfg { static constexpr int RW = 8, NCW = 8, COLS = 256; };   // K <= 9 : 64 x 256 tiles, 9 warps
+template <> struct TmaCfg<16> { static constexpr int RW = 4, NCW = 16, COLS = 128; };   // 64 x 128 tiles, 17 warps
+template <> struct TmaCfg<32> { static constexpr int RW = 4, NCW = 8, COLS = 128; };    // 32 x 128 tiles, 9 warps (FP32-pipe bound anyway)
 template <int K>
 __host__ __device__ constexpr int tma_rows() { return TmaCfg<K>::RW * TmaCfg<K>::NCW; }
 template <int K>
-__host__ __device__ constexpr int tma_stage_bytes() { return (tma_rows<K>() + K) * T_COLS * 4; }
+__host__ __device__ constexpr int tma_stage_bytes() { return (tma_rows<K>() + K) * TmaCfg<K>::COLS * 4; }
 template <int K>
 __host__ __device__ constexpr int tma_nstage() { return (227 * 1024 - 256) / tma_stage_bytes<K>() > 8 ? 8 : (227 * 1024 - 256) / tma_stage_bytes<K>(); }
 
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__((TmaCfg<K>::NCW + 1) * 32, 1)
 k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmRes) {
     constexpr int NST = tma_nstage<K>();
     constexpr int STAGE_F = tma_stage_bytes<K>() / 4; // floats per stage
-    constexpr int RW = TmaCfg<K>::RW, NCW = TmaCfg<K>::NCW, T_ROWS = RW * NCW;
+    constexpr int RW = TmaCfg<K>::RW, NCW = TmaCfg<K>::NCW, T_ROWS = RW * NCW, T_COLS = TmaCfg<K>::COLS;
     extern __shared__ __align__(128) unsigned char g_smem[];
     float *stages = reinterpret_cast<float *>(g_smem);
     uint64_t *full = reinterpret_cast<uint64_t *>(g_smem + (size_t)NST * tma_stage_bytes<K>());
@@ -270,7 +274,7 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     if (warp == NCW) {
         // ------------------------------- producer -------------------------------
         // one elected lane issues two tiled TMA loads per stage: the T_ROWS x 128 block of F and the K x 128 block
-        // of the residual bands (tiles never straddle an exchange block: n is a multiple of 128 when G > 1, and a
+        // of the residual bands (tiles never straddle an exchange block: n is a multiple of 256 when G > 1, and a
         // single block's tail beyond n is zero-filled by the TMA unit)
         if (lane == 0) {
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -307,8 +311,9 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
             for (int s = 0; s < nstep; s++, it++) {
                 const int st = it % NST;
                 mbar_wait(&full[st], (it / NST) & 1);
-                const float *sf = stages + (size_t)st * STAGE_F + lane * 4;
-                {
+#pragma unroll
+                for (int hcol = 0; hcol < T_COLS; hcol += 128) { // a lane covers 4 columns of every 128
+                    const float *sf = stages + (size_t)st * STAGE_F + lane * 4 + hcol;
                     float4 f[RW];
 #pragma unroll
                     for (int r = 0; r < RW; r++) f[r] = *reinterpret_cast<const float4 *>(sf + (warp * RW + r) * T_COLS);
@@ -571,11 +576,11 @@ static int make_maps(daisy_solver *s) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { daisy_set_error("cuTensorMapEncodeTiled is not available from this driver"); return DAISY_E_CUDA; }
     daisy_ctx *c = s->ctx;
-    int trows = (s->Kp == 32) ? 32 : 64;
+    const int trows = (s->Kp == 32) ? 32 : 64, tcols = (s->Kp <= 9) ? 256 : 128; // = tma_rows<Kp>() x TmaCfg<Kp>::COLS
     {
         cuuint64_t dims[2] = { (cuuint64_t)c->ldF, (cuuint64_t)(s->nloc > 0 ? s->nloc : 1) };
         cuuint64_t strides[1] = { (cuuint64_t)c->ldF * 4 };
-        cuuint32_t box[2] = { 128, (cuuint32_t)trows };
+        cuuint32_t box[2] = { (cuuint32_t)tcols, (cuuint32_t)trows };
         cuuint32_t es[2] = { 1, 1 };
         CUresult r = enc(&s->tmF, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, c->d_F, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -584,7 +589,7 @@ static int make_maps(daisy_solver *s) {
     for (int b = 0; b < 2; b++) {
         cuuint64_t dims[3] = { (cuuint64_t)s->n, (cuuint64_t)s->Kp, (cuuint64_t)s->G };
         cuuint64_t strides[2] = { (cuuint64_t)s->n * 4, (cuuint64_t)s->bstride * 4 };
-        cuuint32_t box[3] = { 128, (cuuint32_t)s->Kp, 1 };
+        cuuint32_t box[3] = { (cuuint32_t)tcols, (cuuint32_t)s->Kp, 1 };
         cuuint32_t es[3] = { 1, 1, 1 };
         CUresult r = enc(&s->tmRes[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, s->d_res[b], dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -18,9 +18,9 @@ from . import _lib
 def partition(N: int, rank: int, nranks: int):
     """(row0, row1, rows_per_rank) -- must match ``set_partition`` in csrc/api.cu."""
     n = (N + nranks - 1) // nranks
-    # one block: multiple of 4 floats (16-byte TMA alignment); several: multiple of 128 so that a 128-column TMA
+    # one block: multiple of 4 floats (16-byte TMA alignment); several: multiple of 256 so that a 256-column TMA
     # tile of the residual never straddles two ranks' blocks
-    n = max(4, (n + 127) // 128 * 128 if nranks > 1 else (n + 3) // 4 * 4)
+    n = max(4, (n + 255) // 256 * 256 if nranks > 1 else (n + 3) // 4 * 4)
     return min(N, rank * n), min(N, (rank + 1) * n), n
 
 

@@ -142,9 +142,9 @@ def test_matrix_cache_file_format(tmp_path):
 
 def test_partition_and_exchange_layout():
     assert dist.partition(131072, 3, 8) == (49152, 65536, 16384)
-    assert dist.partition(7712, 7, 8) == (7168, 7712, 1024)  # 964 rounded up to a multiple of 128; last block is short
+    assert dist.partition(7712, 7, 8) == (7168, 7712, 1024)  # 964 rounded up to a multiple of 256; last block is short
     assert dist.partition(6401, 0, 1) == (0, 6401, 6404)     # single block: multiple of 4
-    assert dist.partition(10, 3, 4) == (10, 10, 128)         # more blocks than rows: empty tail ranks
+    assert dist.partition(10, 3, 4) == (10, 10, 256)         # more blocks than rows: empty tail ranks
     assert dist.block_layout(9, 964) == (8696, 8676)         # K*n floats + K doubles, padded to 16 B
     assert [dist.padded_K(k) for k in (1, 2, 3, 9, 12, 17, 32)] == [1, 3, 3, 9, 16, 32, 32]
     x = api.cie1931WavelengthToXYZFit(550.0)
