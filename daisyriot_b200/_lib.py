@@ -43,6 +43,7 @@ SYMBOLS = {
     "daisy_ctx_set_stream": (_i, [_vp, _vp]),
     "daisy_query_closest": (_i, [_vp, _i, _fp, _vp]),
     "daisy_query_closest_device": (_i, [_vp, _i, _vp, _vp]),
+    "daisy_trace_screen": (_i, [_vp, _i, _i, _i, _fp, _fp, _fp, _i, _fp, _vp]),
     "daisy_unoccluded_rows": (_i, [_vp, _i, _i, _i, _vp]),
     "daisy_formfactors_build": (_i, [_vp, _i]),
     "daisy_formfactors_ld": (_i, [_vp, _i64p]),
@@ -50,6 +51,7 @@ SYMBOLS = {
     "daisy_formfactors_to_csc": (_i, [_vp, _i64p, _fp, _ip, _ip]),
     "daisy_formfactors_write_rows": (_i, [_vp, _i, _i, _fp]),
     "daisy_visibility_masks": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_uint64)]),
+    "daisy_formfactors_row_digest": (_i, [_vp, _i, _i, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "daisy_formfactors_stats": (_i, [_vp, _i64p, _i64p, _i64p, _dp, _dp]),
     "daisy_formfactors_alloc": (_i, [_vp]),
     "daisy_formfactors_ipc_handle": (_i, [_vp, _vp]),

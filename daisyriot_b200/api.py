@@ -85,6 +85,18 @@ class RadMat:
         _lib.check(_lib.lib().daisy_formfactors_read_rows(self._p._ctx, row0, nrows, _lib.fptr(out)), "formfactors_read_rows")
         return out
 
+    def row_digest(self, row0=None, nrows=None):
+        """Exact per-row digests computed on the device (no read-back of the rows): (xor of the float bit patterns,
+        sum of bits*(2c+1) mod 2^64).  :func:`row_digest_host` gives the same from host rows."""
+        r0, r1 = self._p.row_range
+        row0 = r0 if row0 is None else row0
+        nrows = (r1 - row0) if nrows is None else nrows
+        x = np.empty(nrows, np.uint32)
+        w = np.empty(nrows, np.uint64)
+        _lib.check(_lib.lib().daisy_formfactors_row_digest(self._p._ctx, row0, nrows, x.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                           w.ctypes.data_as(C.POINTER(C.c_uint64))), "formfactors_row_digest")
+        return x, w
+
     def to_csc(self):
         """(values, innerIndices, outerStarts) exactly as ``setFromTriplets`` leaves a column-major SparseMatrix."""
         L = _lib.lib()
@@ -270,6 +282,15 @@ class OptixPrimeFunctionality:
         _lib.check(_lib.lib().daisy_formfactors_stats(self._ctx, C.byref(p), C.byref(o), C.byref(r), C.byref(a), C.byref(b)))
         return {"pairs_traced": p.value, "pairs_owned": o.value, "rays": r.value, "lbvh_ms": a.value, "ff_ms": b.value,
                 "pairs_fallback": int(_lib.lib().daisy_formfactors_pairs_fallback(self._ctx))}
+
+
+def row_digest_host(F_rows: np.ndarray):
+    """The digests of :meth:`RadMat.row_digest` from host rows (rows x N float32)."""
+    bits = np.ascontiguousarray(F_rows, np.float32).view(np.uint32)
+    w = (2 * np.arange(bits.shape[1], dtype=np.uint64) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        ws = (bits.astype(np.uint64) * w[None, :]).sum(axis=1, dtype=np.uint64)
+    return np.bitwise_xor.reduce(bits, axis=1), ws
 
 
 def _dot32(a, b) -> np.float32:
@@ -625,35 +646,45 @@ def triangles_per_vertex(mesh: MeshS):
 
 
 def traceScreen(optixP: OptixPrimeFunctionality, camera: Camera, patch_colors: np.ndarray, radiosityRendering: bool = True,
-                antialiasing: bool = True, material_colors: np.ndarray | None = None, rays: np.ndarray | None = None) -> np.ndarray:
+                antialiasing: bool = True, material_colors: np.ndarray | None = None, rays: np.ndarray | None = None,
+                return_hits: bool = False):
     """``OptixPrimeFunctionality::traceScreen`` (.cpp:83-131): returns ``optixView`` as (H, W, 3) float32.
-    ``patch_colors`` = ``lightning.get_color_of_patch`` for every patch (N,3)."""
+    ``patch_colors`` = ``lightning.get_color_of_patch`` for every patch (N,3); with ``radiosityRendering=False`` the frame
+    shows ``material_colors[materialIndexPerTriangle]`` instead.  Closest hit, ``isFacingBack``, ``Drawer::interpolate``,
+    the supersample average and the clamp all run in one kernel (``daisy_trace_screen``); ``return_hits=True`` also hands
+    back the hit records (what the reference files into ``trianglesonScreen`` for picking)."""
     mesh = optixP.mesh
     samples = camera.supersampling if antialiasing else 1
-    rays = camera.gen_rays_for_screen(antialiasing) if rays is None else np.ascontiguousarray(rays, np.float32)
-    hits = optixP.optixQuery(rays.shape[0], rays)
-    tid = hits["triangleId"]
-    hit = hits["t"] > 0
-    T = mesh.triangleIndices
-    safe = np.where(hit, tid, 0)
-    # triangle_math::isFacingBack(eye, triangleId): dot(normalize(centre - eye), avgNormal) >= 0      triangle_math.cpp:76-86
-    a, b, c = (mesh.vertices[T[safe, k]] for k in range(3))
-    centre = ((a + b + c) / np.float32(3)).astype(np.float32)
-    n = (mesh.normals[T[safe, 3]] + mesh.normals[T[safe, 4]] + mesh.normals[T[safe, 5]]) / np.float32(3)
-    n = n / np.linalg.norm(n, axis=1, keepdims=True)
-    d = centre - camera.eye[None, :]
-    d = d / np.linalg.norm(d, axis=1, keepdims=True)
-    front = hit & ~((d * n).sum(1) >= 0)
+    rays = np.ascontiguousarray(camera.gen_rays_for_screen(antialiasing) if rays is None else rays, np.float32)
+    W, H = camera.pixwidth, camera.pixheight
+    if rays.reshape(-1, 6).shape[0] != W * H * samples:
+        raise ValueError("rays must hold width*height*samples origin/direction pairs")
     if radiosityRendering:
-        # Drawer::interpolate: colours averaged per vertex over trianglesPerVertex, weighted u*a + v*b + (1-u-v)*c
-        off, tris = triangles_per_vertex(mesh)
-        csum = np.concatenate([np.zeros((1, 3), np.float64), np.cumsum(patch_colors[tris].astype(np.float64), axis=0)])
-        cnt = np.maximum(off[1:] - off[:-1], 1)[:, None]
-        vcol = ((csum[off[1:]] - csum[off[:-1]]) / cnt).astype(np.float32)
-        u, v = hits["u"][:, None], hits["v"][:, None]
-        col = u * vcol[T[safe, 0]] + v * vcol[T[safe, 1]] + (np.float32(1) - u - v) * vcol[T[safe, 2]]
+        rgb = np.ascontiguousarray(patch_colors, np.float32)
     else:
-        col = material_colors[mesh.materialIndexPerTriangle[safe]]
-    col = np.where(front[:, None], col, np.float32(0)).astype(np.float32)
-    img = col.reshape(camera.pixheight, camera.pixwidth, samples, 3).sum(2) / np.float32(samples)
-    return np.clip(img, 0.0, 1.0).astype(np.float32)
+        rgb = np.ascontiguousarray(np.asarray(material_colors, np.float32)[mesh.materialIndexPerTriangle], np.float32)
+    if rgb.shape != (mesh.numtriangles, 3):
+        raise ValueError("one RGB colour per patch is needed")
+    out = np.empty((H, W, 3), np.float32)
+    hits = np.empty(W * H * samples, HIT_DTYPE) if return_hits else None
+    eye = np.ascontiguousarray(camera.eye, np.float32)
+    _lib.check(_lib.lib().daisy_trace_screen(optixP._ctx, W, H, samples, _lib.fptr(rays), _lib.fptr(eye), _lib.fptr(rgb),
+                                             1 if radiosityRendering else 0, _lib.fptr(out),
+                                             hits.ctypes.data if return_hits else None), "trace_screen")
+    return (out, hits) if return_hits else out
+
+
+def write_png(path: str, img: np.ndarray) -> None:
+    """Headless stand-in for the reference's ``i`` key (``InputHandler`` -> ``ImageExporter::saveImage``): ``optixView`` as an
+    8-bit RGB PNG, bottom row first like the OpenGL read-back (stdlib only: zlib + struct)."""
+    import zlib
+    a = (np.clip(np.asarray(img, np.float32), 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)[::-1]
+    h, w, _ = a.shape
+    raw = b"".join(b"\x00" + a[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))

@@ -31,7 +31,7 @@ static void free_ctx(daisy_ctx *c) {
         for (int g = 0; g < c->nranks && g < 16; g++)
             if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
     cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane); cudaFree(c->d_pid);
-    cudaFree(c->d_nodes); cudaFree(c->d_F);
+    cudaFree(c->d_nodes); cudaFree(c->d_F); cudaFree(c->d_order); free(c->h_order); cudaFree(c->d_vadj_off); cudaFree(c->d_vadj);
     delete c;
 }
 
@@ -114,6 +114,21 @@ extern "C" int daisy_ctx_create(const float *vertices, int nv, const float *norm
         CC(cudaMalloc(&c->d_pid, sizeof(int) * pid.size()));
         CC(cudaMemcpy(c->d_pid, pid.data(), sizeof(int) * pid.size(), cudaMemcpyHostToDevice));
     }
+    {
+        // MeshS::trianglesPerVertex (MeshS.cpp:107-109) as CSR, lists in ascending triangle order: Drawer::interpolate sums
+        // the patch colours of a vertex in exactly that order
+        std::vector<int> off((size_t)nv + 1, 0), adj((size_t)3 * (ntri > 0 ? ntri : 1), 0);
+        for (int i = 0; i < ntri; i++)
+            for (int k = 0; k < 3; k++) off[(size_t)tri_idx[6 * (size_t)i + k] + 1]++;
+        for (int v = 0; v < nv; v++) off[(size_t)v + 1] += off[v];
+        std::vector<int> fill(off.begin(), off.end() - 1);
+        for (int i = 0; i < ntri; i++)
+            for (int k = 0; k < 3; k++) adj[(size_t)fill[tri_idx[6 * (size_t)i + k]]++] = i;
+        CC(cudaMalloc(&c->d_vadj_off, sizeof(int) * off.size()));
+        CC(cudaMalloc(&c->d_vadj, sizeof(int) * adj.size()));
+        CC(cudaMemcpy(c->d_vadj_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice));
+        CC(cudaMemcpy(c->d_vadj, adj.data(), sizeof(int) * adj.size(), cudaMemcpyHostToDevice));
+    }
 #undef CC
     int rc = dz_build_lbvh(c);
     if (!rc) rc = dz_precompute_geom(c);
@@ -141,7 +156,9 @@ extern "C" int daisy_ctx_set_samples(daisy_ctx *ctx, const float *uv, int S) {
 extern "C" int daisy_ctx_set_partition(daisy_ctx *ctx, int rank, int nranks) {
     DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_ctx_set_partition: null context");
     DZ_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, DAISY_E_INVALID, "daisy_ctx_set_partition: bad rank/nranks");
-    DZ_REQUIRE(!ctx->have_F, DAISY_E_STATE, "daisy_ctx_set_partition: form factors already built");
+    // the matrix allocation, its leading dimension and any IPC mapping handed to peers are sized from the row range
+    DZ_REQUIRE(!ctx->have_F && !ctx->d_F && !ctx->peers_set, DAISY_E_STATE,
+               "daisy_ctx_set_partition: form factors already allocated or built (set the partition before daisy_formfactors_alloc/build/write_rows)");
     set_partition(ctx, rank, nranks);
     return DAISY_OK;
 }
@@ -265,7 +282,6 @@ extern "C" int daisy_formfactors_set_peers(daisy_ctx *ctx, const void *handles, 
     DZ_REQUIRE(ctx && handles, DAISY_E_INVALID, "daisy_formfactors_set_peers: null argument");
     DZ_REQUIRE(nranks == ctx->nranks && nranks <= 16, DAISY_E_INVALID, "daisy_formfactors_set_peers: nranks must match the partition (<= 16)");
     DZ_REQUIRE(ctx->d_F && !ctx->peers_set, DAISY_E_STATE, "daisy_formfactors_set_peers: allocate first, set once");
-    DZ_REQUIRE(ctx->rows_per_rank % 64 == 0, DAISY_E_STATE, "daisy_formfactors_set_peers: rows per rank must be a multiple of the tile size");
     DZ_CUDA(cudaSetDevice(ctx->device));
     for (int g = 0; g < nranks; g++) {
         if (g == ctx->rank) { ctx->peerF[g] = ctx->d_F; continue; }
@@ -368,6 +384,50 @@ extern "C" int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int
     cudaFree(d);
     if (e != cudaSuccess) { daisy_set_error("daisy_visibility_masks: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
     return rc;
+}
+
+// ---- per-row digests of the resident matrix (parity evidence at sizes whose matrix does not fit the host) ----------
+// one warp per row; both digests are exact integer reductions, hence independent of the summation order:
+//   xor_out[r]  = XOR over columns of the float bit patterns
+//   wsum_out[r] = SUM over columns of bits * (2c + 1) mod 2^64   (position sensitive)
+__global__ void k_row_digest(const float *__restrict__ F, int64_t ldF, int N, int nrows, uint32_t *__restrict__ xo, unsigned long long *__restrict__ wo) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const float *src = F + (size_t)row * ldF;
+    uint32_t x = 0;
+    unsigned long long w = 0;
+    for (int c = lane; c < N; c += 32) {
+        const uint32_t b = __float_as_uint(src[c]);
+        x ^= b;
+        w += (unsigned long long)b * (unsigned long long)(2 * (long long)c + 1);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        x ^= __shfl_xor_sync(0xffffffffu, x, o);
+        w += __shfl_xor_sync(0xffffffffu, w, o);
+    }
+    if (lane == 0) { xo[row] = x; wo[row] = w; }
+}
+
+extern "C" int daisy_formfactors_row_digest(daisy_ctx *ctx, int row0, int nrows, uint32_t *xor_out, uint64_t *wsum_out) {
+    DZ_REQUIRE(ctx && (nrows == 0 || (xor_out && wsum_out)), DAISY_E_INVALID, "daisy_formfactors_row_digest: null argument");
+    DZ_REQUIRE(ctx->have_F, DAISY_E_STATE, "daisy_formfactors_row_digest: no form factors yet");
+    DZ_REQUIRE(nrows >= 0 && row0 >= ctx->row0 && row0 + nrows <= ctx->row1, DAISY_E_INVALID, "daisy_formfactors_row_digest: rows outside this context's range");
+    if (nrows == 0) return DAISY_OK;
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    uint32_t *dx = nullptr;
+    unsigned long long *dw = nullptr;
+    DZ_CUDA(cudaMalloc(&dx, sizeof(uint32_t) * (size_t)nrows));
+    cudaError_t e = cudaMalloc(&dw, sizeof(unsigned long long) * (size_t)nrows);
+    if (e == cudaSuccess) {
+        k_row_digest<<<(nrows + 7) / 8, 256, 0, ctx->stream>>>(ctx->d_F + (size_t)(row0 - ctx->row0) * ctx->ldF, ctx->ldF, ctx->N, nrows, dx, dw);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(xor_out, dx, sizeof(uint32_t) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(wsum_out, dw, sizeof(uint64_t) * (size_t)nrows, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dx); cudaFree(dw);
+    if (e != cudaSuccess) { daisy_set_error("daisy_formfactors_row_digest: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
+    return DAISY_OK;
 }
 
 extern "C" int64_t daisy_formfactors_pairs_fallback(daisy_ctx *ctx) { return ctx ? ctx->pairs_heavy : -1; }

@@ -5,7 +5,9 @@
 // morton -> bitonic sort -> hierarchy -> bottom-up refit -> node packing, all on the device;
 // `query->execute()` becomes one thread per ray walking that hierarchy.
 #include "daisy_common.cuh"
+#include "closest.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 // ---------------------------------------------------------------------------------------------------------
@@ -179,6 +181,13 @@ __global__ void k_pack_nodes(const uint64_t *__restrict__ keys, int N, const int
     nodes[i] = n;
 }
 
+// tile composition for the form-factor kernel: sorted Morton order (spatially compact groups of 64) or the caller's order
+__global__ void k_tile_order(const uint64_t *__restrict__ keys, int N, int nslots, int morton, int *__restrict__ order) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    order[p] = p < N ? (morton ? (int)(uint32_t)keys[p] : p) : -1;
+}
+
 int dz_build_lbvh(daisy_ctx *ctx) {
     int N = ctx->N;
     cudaStream_t st = ctx->stream;
@@ -189,6 +198,10 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     DZ_CUDA(cudaMalloc(&ctx->d_triverts, sizeof(TriVerts) * (size_t)(N > 0 ? N : 1)));
     DZ_CUDA(cudaMalloc(&ctx->d_nodes, sizeof(BvhNode) * (size_t)(N > 1 ? N - 1 : 1)));
     DZ_CUDA(cudaMalloc(&ctx->d_tribox, sizeof(float4) * 2 * (size_t)(N > 0 ? N : 1)));
+    ctx->nslots = ((N + 63) / 64) * 64;
+    DZ_CUDA(cudaMalloc(&ctx->d_order, sizeof(int) * (size_t)(ctx->nslots > 0 ? ctx->nslots : 1)));
+    ctx->h_order = (int *)malloc(sizeof(int) * (size_t)(ctx->nslots > 0 ? ctx->nslots : 1));
+    if (!ctx->h_order) { daisy_set_error("out of host memory"); return DAISY_E_NOMEM; }
     if (N == 0) { ctx->root = 0; DZ_CUDA(cudaEventDestroy(e0)); DZ_CUDA(cudaEventDestroy(e1)); return DAISY_OK; }
     int npad = BITONIC_BLOCK;
     while (npad < N) npad <<= 1;
@@ -218,8 +231,14 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     } else {
         ctx->root = ~0; // single triangle: the root is the leaf of triangle 0
     }
+    {
+        const char *e = getenv("DAISY_FF_ORDER"); // "identity": tiles of 64 consecutive caller indices (A/B switch; results are identical)
+        const int morton = !(e && e[0] == 'i');
+        k_tile_order<<<(ctx->nslots + 255) / 256, 256, 0, st>>>(d_keys, N, ctx->nslots, morton, ctx->d_order);
+    }
     DZ_CUDA(cudaGetLastError());
     DZ_CUDA(cudaEventRecord(e1, st));
+    DZ_CUDA(cudaMemcpyAsync(ctx->h_order, ctx->d_order, sizeof(int) * (size_t)ctx->nslots, cudaMemcpyDeviceToHost, st));
     DZ_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -231,52 +250,14 @@ int dz_build_lbvh(daisy_ctx *ctx) {
 
 // ---------------------------------------------------------------------------------------------------------
 // closest hit: (t, triangleId) lexicographic minimum over all triangles the watertight test accepts with t > 0
+// (device routine in closest.cuh, shared with the traceScreen kernel in trace.cu)
 __global__ void __launch_bounds__(128) k_closest(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root,
                                                  int ntri, int n, const float *__restrict__ rays, daisy_hit *__restrict__ hits) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     f3 o = mk3(rays[6 * (size_t)i], rays[6 * (size_t)i + 1], rays[6 * (size_t)i + 2]);
     f3 d = mk3(rays[6 * (size_t)i + 3], rays[6 * (size_t)i + 4], rays[6 * (size_t)i + 5]);
-    daisy_hit best; best.t = -1.0f; best.triangleId = -1; best.u = 0.f; best.v = 0.f;
-    if (ntri > 0) {
-        WRay w = wray_setup(o, d);
-        f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-        int stack[64];
-        int sp = 0;
-        int cur = root;
-        while (true) {
-            if (cur < 0) {
-                int k = ~cur;
-                TriVerts t = tv[k];
-                float tt, uu, vv;
-                if (wray_tri(w, xyz(t.a), xyz(t.b), xyz(t.c), tt, uu, vv)) {
-                    if (best.triangleId < 0 || tt < best.t || (tt == best.t && k < best.triangleId)) {
-                        best.t = tt; best.triangleId = k; best.u = uu; best.v = vv;
-                    }
-                }
-                if (sp == 0) break;
-                cur = stack[--sp];
-                continue;
-            }
-            BvhNode nd = nodes[cur];
-            float tmax = best.triangleId >= 0 ? best.t : INFINITY;
-            float tl, tr;
-            bool hl = ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, tmax, tl);
-            bool hr = ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, tmax, tr);
-            if (hl && hr) {
-                int nearc = nd.d.x, farc = nd.d.y;
-                if (tr < tl) { nearc = nd.d.y; farc = nd.d.x; }
-                stack[sp++] = farc;
-                cur = nearc;
-            } else if (hl) cur = nd.d.x;
-            else if (hr) cur = nd.d.y;
-            else {
-                if (sp == 0) break;
-                cur = stack[--sp];
-            }
-        }
-    }
-    hits[i] = best;
+    hits[i] = closest_hit(nodes, tv, root, ntri, o, d);
 }
 
 int dz_launch_closest(daisy_ctx *ctx, int n, const float *d_rays, daisy_hit *d_hits) {

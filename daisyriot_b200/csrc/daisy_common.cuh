@@ -210,9 +210,14 @@ struct daisy_ctx {
     // device mesh
     float *d_vertices = nullptr, *d_normals = nullptr;
     int *d_tri = nullptr;
+    int *d_vadj_off = nullptr, *d_vadj = nullptr; // MeshS::trianglesPerVertex as CSR: triangles using vertex v, ascending ids
     TriVerts *d_triverts = nullptr;
     float4 *d_tribox = nullptr; // padded per-triangle boxes (2 float4 each), same boxes as the LBVH leaves
     PatchGeom *d_geom = nullptr;
+    int *d_order = nullptr;     // tile composition of the form-factor kernel: slot p of the tile grid holds triangle d_order[p]
+                                // (Morton order of the LBVH build => 64 consecutive slots are spatially compact); -1 = empty slot
+    int *h_order = nullptr;     // host copy (job lists of row-restricted runs)
+    int nslots = 0;             // slots = ceil(N / 64) * 64
     int *d_pid = nullptr;       // per triangle: id (>= 1) of the axis-aligned plane all three vertices lie in EXACTLY, 0 if none
     float4 *d_plane = nullptr;  // per triangle: unit geometric normal, w = smallest altitude if coplanar skipping is safe for it, else -1
     float ext = 0.f;            // largest scene extent

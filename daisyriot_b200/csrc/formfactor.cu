@@ -13,6 +13,7 @@
 #include "daisy_common.cuh"
 #include <math.h>
 #include <stdlib.h>
+#include <vector>
 
 #define TILE 64
 #define FF_THREADS 256
@@ -575,6 +576,7 @@ struct FFParams {
     const float4 *tribox; // padded triangle boxes, 2 float4 per triangle
     const float4 *plane;  // per-triangle plane record (k_tri_planes)
     const int *pid;       // per-triangle exact axis-aligned plane id (0 = none)
+    const int *order;     // tile composition: slot -> triangle id (-1 = empty slot); tile T holds slots [64 T, 64 T + 64)
     float tau;            // coplanarity tolerance
     int n_inner;          // samples [0, n_inner) of the device-order pattern are inner samples
     int ring_on;          // coplanar skipping enabled
@@ -583,9 +585,8 @@ struct FFParams {
     int row0, row1;      // rows this context owns
     float *F;            // (row1-row0) x ldF, may be null (mask-only run)
     int64_t ldF;
-    // peer mode (multi-GPU): every upper-triangle tile is computed by exactly one rank, which stores the tile into the
-    // row owner's F and the mirrored tile into the column owner's F -- its own memory or a peer's, mapped through CUDA
-    // IPC and written over NVLink
+    // peer mode (multi-GPU): every upper-triangle tile is computed by exactly one rank, which stores every entry into the
+    // row owner's F -- its own memory or a peer's, mapped through CUDA IPC and written over NVLink
     int peer_mode, n_per_rank;
     float *Fpeer[16];
     uint64_t *masks;     // optional (mrow1-mrow0) x N
@@ -597,21 +598,26 @@ struct FFParams {
     const int2 *jobs;    // (row tile, col tile), col tile >= row tile
 };
 
+// Tile slots: [0, 64) = the row-tile's patches, [64, 128) = the column-tile's patches.  A listed pair is (rl, cl) plus a
+// swap bit: visibility rays always run from the patch with the LOWER triangle id to the one with the higher id
+// (OptixPrimeFunctionality.cpp:186-196, row < col), whatever slots the two occupy.
+#define PAIR_SWAP 0x1000
 struct FFSmem {
     // phase 1 (sub-patch records of the row / column patches) and phase 2 (per-warp candidate staging) never overlap in
-    // time, so they share storage: at 75 KB per CTA three CTAs fit one SM
+    // time, so they share storage: three CTAs fit one SM
     union {
-        struct { PatchGeom gr[TILE], gc[TILE]; } p1;
+        struct { PatchGeom g[2 * TILE]; } p1;
         struct {
             int wq[FF_THREADS / 32][FF_QCAP * 32];
             int wk[FF_THREADS / 32][16];
             float4 wb[FF_THREADS / 32][32];
         } p2;
     } u;
-    float area_r[TILE], area_c[TILE]; // patch areas (needed after phase 1 by the host-variant reciprocity rule)
-    TriVerts tr[TILE], tc[TILE];
-    float4 pr[TILE], pc[TILE]; // plane records of the row / column patches
-    int pid_r[TILE], pid_c[TILE]; // their exact plane ids
+    float area[2 * TILE]; // patch areas (needed after phase 1 by the host-variant reciprocity rule)
+    TriVerts tv[2 * TILE];
+    float4 pl[2 * TILE];  // plane records
+    int pid[2 * TILE];    // exact plane ids
+    int id[2 * TILE];     // triangle ids of the slots, -1 = empty
     unsigned char perm[DAISY_MAX_SAMPLES];
     float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
     float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
@@ -621,12 +627,23 @@ struct FFSmem {
     float uv[2 * DAISY_MAX_SAMPLES];
 };
 
+#ifdef DAISY_FF_STATS
+#define FF_CLK(slot)                                                                           \
+    do {                                                                                       \
+        const long long now_ = clock64();                                                      \
+        if (lane == 0) atomicAdd(&g_ffstats[24 + (slot)], (unsigned long long)(now_ - clk_)); \
+        clk_ = now_;                                                                           \
+    } while (0)
+#else
+#define FF_CLK(slot) do { } while (0)
+#endif
+
 template <int VARIANT>
 __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
     extern __shared__ __align__(16) unsigned char ff_smem_raw[];
     FFSmem &sm = *reinterpret_cast<FFSmem *>(ff_smem_raw);
-    PatchGeom *s_gr = sm.u.p1.gr, *s_gc = sm.u.p1.gc;
-    TriVerts *s_tr = sm.tr, *s_tc = sm.tc;
+    PatchGeom *s_g = sm.u.p1.g;
+    TriVerts *s_tv = sm.tv;
     float(*s_rc)[TILE + 1] = sm.rc;
     float(*s_cr)[TILE + 1] = sm.cr;
     unsigned short *s_list = sm.list;
@@ -638,6 +655,9 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
     if (tid < DAISY_MAX_SAMPLES) sm.perm[tid] = (unsigned char)c_perm[tid];
     int *my_cand = P.scratch + ((size_t)blockIdx.x * FF_THREADS + tid) * SHAFT_CAP;
     int *warp_cand = P.scratch + ((size_t)blockIdx.x * FF_THREADS + (tid & ~31)) * SHAFT_CAP;
+#ifdef DAISY_FF_STATS
+    long long clk_ = clock64();
+#endif
 
     while (true) {
         if (tid == 0) s_job = atomicAdd(P.job_counter, 1);
@@ -648,63 +668,71 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
         const int R0 = jt.x * TILE, C0 = jt.y * TILE;
         const bool diag = (jt.x == jt.y);
         if (tid == 0) { s_nlist = 0; s_next = 0; s_nown = 0; s_nheavy = 0; s_hnext = 0; }
-        // stage the two patch groups (float4-granular copies: 5 + 3 float4 per patch)
-        for (int i = tid; i < TILE * 5; i += FF_THREADS) {
-            int p = i / 5, q = i - p * 5;
-            int gr = min(R0 + p, P.N - 1), gc = min(C0 + p, P.N - 1);
-            ((float4 *)&s_gr[p])[q] = ((const float4 *)&P.geom[gr])[q];
-            ((float4 *)&s_gc[p])[q] = ((const float4 *)&P.geom[gc])[q];
+        // stage the two patch groups (float4-granular copies: 5 + 3 float4 per patch); empty slots read triangle 0 and are
+        // masked out by id < 0
+        if (tid < 2 * TILE) {
+            const int t = P.order[(tid < TILE ? R0 : C0 - TILE) + tid];
+            const int tt = max(t, 0);
+            sm.id[tid] = t;
+            sm.pl[tid] = P.plane[tt];
+            sm.area[tid] = P.geom[tt].n.w;
+            sm.pid[tid] = P.pid[tt];
         }
-        for (int i = tid; i < TILE * 3; i += FF_THREADS) {
-            int p = i / 3, q = i - p * 3;
-            int gr = min(R0 + p, P.N - 1), gc = min(C0 + p, P.N - 1);
-            ((float4 *)&s_tr[p])[q] = ((const float4 *)&P.tv[gr])[q];
-            ((float4 *)&s_tc[p])[q] = ((const float4 *)&P.tv[gc])[q];
+        for (int i = tid; i < 2 * TILE * 5; i += FF_THREADS) {
+            const int p = i / 5, q = i - p * 5;
+            const int t = max(P.order[(p < TILE ? R0 : C0 - TILE) + p], 0);
+            ((float4 *)&s_g[p])[q] = ((const float4 *)&P.geom[t])[q];
         }
-        if (tid < TILE) { sm.pr[tid] = P.plane[min(R0 + tid, P.N - 1)]; sm.area_r[tid] = P.geom[min(R0 + tid, P.N - 1)].n.w; sm.pid_r[tid] = P.pid[min(R0 + tid, P.N - 1)]; }
-        else if (tid < 2 * TILE) { sm.pc[tid - TILE] = P.plane[min(C0 + tid - TILE, P.N - 1)]; sm.area_c[tid - TILE] = P.geom[min(C0 + tid - TILE, P.N - 1)].n.w; sm.pid_c[tid - TILE] = P.pid[min(C0 + tid - TILE, P.N - 1)]; }
+        for (int i = tid; i < 2 * TILE * 3; i += FF_THREADS) {
+            const int p = i / 3, q = i - p * 3;
+            const int t = max(P.order[(p < TILE ? R0 : C0 - TILE) + p], 0);
+            ((float4 *)&s_tv[p])[q] = ((const float4 *)&P.tv[t])[q];
+        }
         __syncthreads();
 
-        // ---- phase 1: unoccluded form factors of every pair r < c of the tile; facing pairs go on the list
+        // ---- phase 1: unoccluded form factors of every unordered pair of the tile (each once); facing pairs go on the list
         _Pragma("unroll 1") for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
-            int rl = idx >> 6, cl = idx & 63;
-            int r = R0 + rl, c = C0 + cl;
-            bool valid = (r < P.N) && (c < P.N) && (r < c) &&
-                         (P.peer_mode || (r >= P.row0 && r < P.row1) || (c >= P.row0 && c < P.row1));
+            const int rl = idx >> 6, cl = idx & 63;
+            const int r = sm.id[rl], c = sm.id[TILE + cl];
+            const bool valid = (r >= 0) && (c >= 0) && (diag ? rl < cl : true) &&
+                               (P.peer_mode || (r >= P.row0 && r < P.row1) || (c >= P.row0 && c < P.row1));
             float f_rc = 0.0f, f_cr = 0.0f;
             bool trace = false;
             if (valid) {
-                ff_pair<VARIANT>(s_gr[rl], s_gc[cl], f_rc, f_cr);
+                ff_pair<VARIANT>(s_g[rl], s_g[TILE + cl], f_rc, f_cr);
                 // calculateRow stores the value only when > 0 (parallellism.cu:101-107)
                 f_rc = (f_rc > 0.0f) ? f_rc : 0.0f;
                 f_cr = (f_cr > 0.0f) ? f_cr : 0.0f;
-                // cuda path: traced iff tripletlist[row*N+col].m_value > 0 (OptixPrimeFunctionality.cpp:190);
-                // per-pair path: every pair is traced and tested after the fact (:335-336) -- same matrix, since
-                // a zero unoccluded factor gives a zero entry either way
-                trace = f_rc > 0.0f;
-                if (!trace) f_cr = 0.0f;
+                // cuda path: traced iff tripletlist[row*N+col].m_value > 0 with row < col (OptixPrimeFunctionality.cpp:190),
+                // i.e. the factor from the lower to the higher triangle id; per-pair path: every pair is traced and tested
+                // after the fact (:335-336) -- same matrix, since a zero unoccluded factor gives a zero entry either way
+                trace = (r < c ? f_rc : f_cr) > 0.0f;
+                if (!trace) { f_rc = 0.0f; f_cr = 0.0f; }
             }
             s_rc[rl][cl] = f_rc;
             s_cr[cl][rl] = f_cr;
+            const int lo_id = min(r, c);
             unsigned m = __ballot_sync(0xffffffffu, trace);
-            unsigned mo = __ballot_sync(0xffffffffu, trace && (P.peer_mode || (r >= P.row0 && r < P.row1)));
+            unsigned mo = __ballot_sync(0xffffffffu, trace && (P.peer_mode || (lo_id >= P.row0 && lo_id < P.row1)));
             if (mo && lane == 0) atomicAdd(&s_nown, __popc(mo));
             if (m) {
                 int base = 0;
                 int leader = __ffs(m) - 1;
                 if (lane == leader) base = atomicAdd(&s_nlist, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (trace) s_list[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)idx;
+                if (trace) s_list[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)(idx | (r > c ? PAIR_SWAP : 0));
             }
         }
         __syncthreads();
         const int nlist = s_nlist;
         if (tid == 0 && nlist) { atomicAdd(P.pair_counter, (unsigned long long)nlist); atomicAdd(P.pair_counter + 1, (unsigned long long)s_nown); }
+        FF_CLK(0);
 
         // ---- phase 2: S visibility rays per listed pair; a warp claims 32 pairs at a time, lane = pair, all lanes
         // trace sample i together (neighbouring pairs + same sample => coherent rays).  First every pair gets a
         // shaft candidate list; pairs whose list fits are resolved against it (2a), the rest walk the LBVH per ray (2b).
-        auto finish_pair = [&](int rl, int cl, int r, int c, uint64_t mask) {
+        auto finish_pair = [&](int rl, int cl, uint64_t mask) {
+            const int r = sm.id[rl], c = sm.id[TILE + cl];
             // visibility = (#hits as float) / RAYS_PER_PATCH                 OptixPrimeFunctionality.cpp:206-211
             float visibility = fd((float)__popcll(mask), (float)P.S);
             float f_rc, f_cr;
@@ -713,9 +741,15 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                 f_rc = __double2float_rn(__dmul_rn((double)visibility, (double)s_rc[rl][cl]));
                 f_cr = __double2float_rn(__dmul_rn((double)visibility, (double)s_cr[cl][rl]));
             } else {
-                // p2pFormfactor returns formfactor*visibility (float); mirrored entry by reciprocity      :165,:343
-                f_rc = fm(s_rc[rl][cl], visibility);
-                f_cr = (f_rc > 0.0f) ? fd(fm(sm.area_r[rl], f_rc), sm.area_c[cl]) : 0.0f;
+                // p2pFormfactor(lo, hi) returns formfactor*visibility (float); the entry of the higher row follows by
+                // reciprocity from the lower one                                                          :165,:343
+                if (r < c) {
+                    f_rc = fm(s_rc[rl][cl], visibility);
+                    f_cr = (f_rc > 0.0f) ? fd(fm(sm.area[rl], f_rc), sm.area[TILE + cl]) : 0.0f;
+                } else {
+                    f_cr = fm(s_cr[cl][rl], visibility);
+                    f_rc = (f_cr > 0.0f) ? fd(fm(sm.area[TILE + cl], f_cr), sm.area[rl]) : 0.0f;
+                }
             }
             if (mask == 0) { f_rc = 0.0f; f_cr = 0.0f; }
             s_rc[rl][cl] = f_rc;
@@ -736,8 +770,9 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
             float m_req = 0.f;
             if (q < nlist) {
                 idx = s_list[q];
-                int rl = idx >> 6, cl = idx & 63;
-                const TriVerts &A = s_tr[rl], &B = s_tc[cl];
+                const int rl = (idx >> 6) & 63, cl = idx & 63;
+                const int ilo = (idx & PAIR_SWAP) ? TILE + cl : rl, ihi = (idx & PAIR_SWAP) ? rl : TILE + cl;
+                const TriVerts &A = s_tv[ilo], &B = s_tv[ihi];
                 Shaft sh = make_shaft(A, B);
                 // premise of coplanar skipping per side: the patch qualifies (plane.w = its smallest altitude h > 0) and every
                 // ray meets its plane steeply.  The ray directions are convex combinations of the three vertex-to-vertex
@@ -748,9 +783,9 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                 // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
                 RingSide rl_, rh_;
                 rl_.on = rh_.on = false;
-                rl_.pid = sm.pid_r[rl]; rh_.pid = sm.pid_c[cl];
+                rl_.pid = sm.pid[ilo]; rh_.pid = sm.pid[ihi];
                 if (P.ring_on) {
-                    const float4 pl = sm.pr[rl], ph = sm.pc[cl];
+                    const float4 pl = sm.pl[ilo], ph = sm.pl[ihi];
                     const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
                     const float d1x = B.b.x - A.b.x, d1y = B.b.y - A.b.y, d1z = B.b.z - A.b.z;
                     const float d2x = B.c.x - A.c.x, d2y = B.c.y - A.c.y, d2z = B.c.z - A.c.z;
@@ -768,30 +803,32 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                     rh_.on = mhi <= EDGE_MARGIN;
                     m_req = fmaxf(rl_.on ? mlo : 0.f, rh_.on ? mhi : 0.f);
                 }
-                ncand = shaft_candidates(P.nodes, P.tv, P.root, sh, rl_, rh_, P.tau, R0 + rl, C0 + cl, my_cand);
+                ncand = shaft_candidates(P.nodes, P.tv, P.root, sh, rl_, rh_, P.tau, sm.id[ilo], sm.id[ihi], my_cand);
                 if (ncand < 0) {
                     const int h = atomicAdd(&s_nheavy, 1);
                     if (h < HEAVY_CAP) s_heavy[h] = (unsigned short)idx;
                     else { // deferral list full (never seen on the benchmark scenes): walk the LBVH per ray right here
                         uint64_t mask = 0;
                         for (int i = 0; i < P.S; i++)
-                            if (ray_sees(P.nodes, P.tv, P.root, A, B, R0 + rl, C0 + cl, c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
-                        finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
+                            if (ray_sees(P.nodes, P.tv, P.root, A, B, sm.id[ilo], sm.id[ihi], c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
+                        finish_pair(rl, cl, mask);
                     }
                 }
             }
             __syncwarp();
+            FF_CLK(1);
             // (ii) lane = sample: the warp resolves its 32 pairs one after the other
             for (int j = 0; j < 32; j++) {
                 const int nc = __shfl_sync(0xffffffffu, ncand, j);
                 if (nc < 0) continue;
                 const int idj = __shfl_sync(0xffffffffu, idx, j);
                 const float mrq = __shfl_sync(0xffffffffu, m_req, j);
-                const int rl = idj >> 6, cl = idj & 63;
-                const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
-                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, C0 + cl, warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, nc >> 16, P.n_inner, mrq,
+                const int rl = (idj >> 6) & 63, cl = idj & 63;
+                const int ilo = (idj & PAIR_SWAP) ? TILE + cl : rl, ihi = (idj & PAIR_SWAP) ? rl : TILE + cl;
+                const TriVerts Tlo = s_tv[ilo], Thi = s_tv[ihi];
+                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, sm.id[ihi], warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, nc >> 16, P.n_inner, mrq,
                                                sm.uv, sm.perm, P.S, lane, sm.u.p2.wq[tid >> 5], sm.u.p2.wk[tid >> 5], sm.u.p2.wb[tid >> 5]);
-                if (lane == 0) finish_pair(rl, cl, R0 + rl, C0 + cl, mask);
+                if (lane == 0) finish_pair(rl, cl, mask);
 #ifdef DAISY_FF_STATS
                 if (lane == 0) {
                     const int nm = nc & 0xffff, pc = __popcll(mask);
@@ -799,11 +836,18 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                     atomicAdd(&g_ffstats[cat], 1ull); atomicAdd(&g_ffstats[4 + cat], (unsigned long long)nm); atomicAdd(&g_ffstats[8 + cat], (unsigned long long)(nc >> 16));
                     if (nm == 0 && pc == P.S) atomicAdd(&g_ffstats[12], 1ull);
                 }
+                {
+                    const int nm = nc & 0xffff;
+                    const long long now_ = clock64();
+                    if (lane == 0) atomicAdd(&g_ffstats[nm == 0 ? 26 : 27], (unsigned long long)(now_ - clk_));
+                    clk_ = now_;
+                }
 #endif
             }
             __syncwarp();
         }
         __syncthreads();
+        FF_CLK(4);
         const int nheavy = min(s_nheavy, HEAVY_CAP);
         if (tid == 0 && s_nheavy) atomicAdd(P.pair_counter + 2, (unsigned long long)s_nheavy);
         while (true) { // 2b
@@ -813,53 +857,48 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
             if (q0 >= nheavy) break;
             int q = q0 + lane;
             if (q < nheavy) {
-                int idx = s_heavy[q];
-                int rl = idx >> 6, cl = idx & 63;
-                int r = R0 + rl, c = C0 + cl;
-                const TriVerts Tlo = s_tr[rl], Thi = s_tc[cl];
+                const int idx = s_heavy[q];
+                const int rl = (idx >> 6) & 63, cl = idx & 63;
+                const int ilo = (idx & PAIR_SWAP) ? TILE + cl : rl, ihi = (idx & PAIR_SWAP) ? rl : TILE + cl;
+                const TriVerts Tlo = s_tv[ilo], Thi = s_tv[ihi];
                 uint64_t mask = 0;
                 for (int i = 0; i < P.S; i++)
-                    if (ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, r, c, c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
-                finish_pair(rl, cl, r, c, mask);
+                    if (ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, sm.id[ilo], sm.id[ihi], c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
+                finish_pair(rl, cl, mask);
             }
         }
         __syncthreads();
+        FF_CLK(5);
 
-        // ---- phase 3: coalesced tile stores.  Rows of s_rc are rows R0.. of F; rows of s_cr are rows C0.. of F.
-        if (P.F && P.peer_mode) {
-            const int ga = R0 / P.n_per_rank, gb = C0 / P.n_per_rank; // tiles never straddle two ranks (n is a multiple of 128)
-            float *Fa = P.Fpeer[ga] - (size_t)ga * P.n_per_rank * P.ldF;
-            float *Fb = P.Fpeer[gb] - (size_t)gb * P.n_per_rank * P.ldF;
+        // ---- phase 3: tile stores.  Row a of s_rc is row id[a] of F; row a of s_cr is row id[64 + a] of F.  With Morton
+        // tiles the columns of one row are short runs of consecutive triangle ids (a few sectors per row), not one segment
+        if (P.F) {
             _Pragma("unroll 1") for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
-                int a = idx >> 6, b = idx & 63;
-                if (diag) {
-                    int r = R0 + a, c = C0 + b;
-                    if (r < P.N && c < P.N) Fa[(size_t)r * P.ldF + c] = (a < b) ? s_rc[a][b] : ((a > b) ? s_cr[a][b] : 0.0f);
-                } else {
-                    int r = R0 + a, c = C0 + b;
-                    if (r < P.N && c < P.N) Fa[(size_t)r * P.ldF + c] = s_rc[a][b];
-                    int r2 = C0 + a, c2 = R0 + b; // mirrored tile: row = column patch
-                    if (r2 < P.N && c2 < P.N) Fb[(size_t)r2 * P.ldF + c2] = s_cr[a][b];
-                }
-            }
-        } else if (P.F) {
-            _Pragma("unroll 1") for (int idx = tid; idx < TILE * TILE; idx += FF_THREADS) {
-                int a = idx >> 6, b = idx & 63;
-                if (diag) {
-                    int r = R0 + a, c = C0 + b;
-                    if (r < P.N && c < P.N && r >= P.row0 && r < P.row1) {
-                        float v = (a < b) ? s_rc[a][b] : ((a > b) ? s_cr[a][b] : 0.0f);
-                        P.F[(size_t)(r - P.row0) * P.ldF + c] = v;
+                const int a = idx >> 6, b = idx & 63;
+                {
+                    const int r = sm.id[a], c = sm.id[TILE + b];
+                    if (r >= 0 && c >= 0) {
+                        const float v = diag ? ((a < b) ? s_rc[a][b] : ((a > b) ? s_cr[a][b] : 0.0f)) : s_rc[a][b];
+                        if (P.peer_mode) {
+                            const int g = r / P.n_per_rank;
+                            P.Fpeer[g][(size_t)(r - g * P.n_per_rank) * P.ldF + c] = v;
+                        } else if (r >= P.row0 && r < P.row1) P.F[(size_t)(r - P.row0) * P.ldF + c] = v;
                     }
-                } else {
-                    int r = R0 + a, c = C0 + b;
-                    if (r < P.N && c < P.N && r >= P.row0 && r < P.row1) P.F[(size_t)(r - P.row0) * P.ldF + c] = s_rc[a][b];
-                    int r2 = C0 + a, c2 = R0 + b; // mirrored tile: row = column patch
-                    if (r2 < P.N && c2 < P.N && r2 >= P.row0 && r2 < P.row1) P.F[(size_t)(r2 - P.row0) * P.ldF + c2] = s_cr[a][b];
+                }
+                if (!diag) { // mirrored tile: row = column patch
+                    const int r = sm.id[TILE + a], c = sm.id[b];
+                    if (r >= 0 && c >= 0) {
+                        const float v = s_cr[a][b];
+                        if (P.peer_mode) {
+                            const int g = r / P.n_per_rank;
+                            P.Fpeer[g][(size_t)(r - g * P.n_per_rank) * P.ldF + c] = v;
+                        } else if (r >= P.row0 && r < P.row1) P.F[(size_t)(r - P.row0) * P.ldF + c] = v;
+                    }
                 }
             }
         }
         __syncthreads();
+        FF_CLK(6);
     }
 }
 
@@ -871,15 +910,19 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     // row range of interest: the context's rows when writing F, else the mask rows
     int r0 = write_F ? ctx->row0 : mrow0, r1 = write_F ? ctx->row1 : mrow1;
     if (r1 <= r0 && !(write_F && ctx->peers_set)) return DAISY_OK;
-    int t0 = r0 / TILE, t1 = (r1 - 1) / TILE; // tiles overlapping the range
-    // jobs: upper-triangle tiles (R <= C).  Local mode: every tile with R or C inside this context's rows [t0, t1]
-    // (off-diagonal blocks are then traced by both owners).  Peer mode: every tile is traced by exactly one rank, chosen by a
-    // hash of (R, C) -- any rank can store a tile and its mirror into the two owners' matrices through the IPC mappings, and
-    // tile cost varies by orders of magnitude with the geometry (wall-to-wall blocks vs blocks of one plane), so spreading
-    // the ~ntiles^2/2 tiles pseudo-randomly is what balances the ranks (owner-based assignment left 8 GPUs at 4.5x).
+    // jobs: upper-triangle tiles (R <= C) of the slot grid.  Local mode: every tile one of whose two patch groups holds a row
+    // of the range of interest (off-diagonal blocks are then traced by both owners).  Peer mode: every tile is traced by
+    // exactly one rank, chosen by a hash of (R, C) -- any rank can store any entry into its owner's matrix through the IPC
+    // mappings, and tile cost varies by orders of magnitude with the geometry (wall-to-wall blocks vs blocks of one plane),
+    // so spreading the ~ntiles^2/2 tiles pseudo-randomly is what balances the ranks (owner-based assignment left 8 GPUs at 4.5x).
     const bool peer = write_F && ctx->peers_set && ctx->nranks > 1;
+    std::vector<char> has((size_t)ntiles, 0);
+    for (int p = 0; p < ctx->nslots; p++) {
+        const int t = ctx->h_order[p];
+        if (t >= r0 && t < r1) has[(size_t)(p / TILE)] = 1;
+    }
     auto mine = [&](int R, int C) -> bool {
-        if (!peer) return (R >= t0 && R <= t1) || (C >= t0 && C <= t1);
+        if (!peer) return has[(size_t)R] || has[(size_t)C];
         const uint32_t h = ((uint32_t)R * 0x9E3779B1u) ^ ((uint32_t)C * 0x85EBCA77u);
         return (int)((h >> 12) % (uint32_t)ctx->nranks) == ctx->rank;
     };
@@ -904,6 +947,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     DZ_CUDA(cudaMemsetAsync(d_pairs, 0, 3 * sizeof(unsigned long long), st));
     FFParams P;
     P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.tribox = ctx->d_tribox; P.scratch = nullptr; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
+    P.order = ctx->d_order;
     P.plane = ctx->d_plane; P.pid = ctx->d_pid; P.tau = COPLANAR_TAU * ctx->ext; P.n_inner = ctx->n_nonedge;
     { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
     P.row0 = r0; P.row1 = r1;
@@ -949,6 +993,12 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
         fprintf(stderr, "ffstats simple&fully-visible %llu ; slab iterations pass0 %llu pass1 %llu\n", h[12], h[16], h[17]);
         fprintf(stderr, "ffstats flush: rounds executed %llu, rounds if balanced over lanes %llu, tests queued %llu (%.1f lanes per executed round)\n",
                 h[22], h[20], h[21], h[22] ? (double)h[21] / h[22] : 0.0);
+        {
+            const char *ph[7] = { "stage+phase1", "shaft walk", "samples(simple)", "samples(listed)", "tile barrier wait", "per-ray fallback", "tile store" };
+            unsigned long long tot = 0;
+            for (int i = 0; i < 7; i++) tot += h[24 + i];
+            for (int i = 0; i < 7; i++) fprintf(stderr, "ffstats warp-cycles %-18s %6.2f %%\n", ph[i], tot ? 100.0 * (double)h[24 + i] / (double)tot : 0.0);
+        }
         unsigned long long z[32] = { 0 };
         cudaMemcpyToSymbol(g_ffstats, z, sizeof(z));
     }

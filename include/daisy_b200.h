@@ -55,8 +55,10 @@ void daisy_ctx_destroy(daisy_ctx *ctx);
  * draws it from rand() seeded by wall-clock time, so the drop-in takes it as an input. */
 int daisy_ctx_set_samples(daisy_ctx *ctx, const float *uv, int S);
 /* multi-GPU (one process per GPU): this context builds and owns the row block `rank` of `nranks` equal blocks of
- * rows_per_rank = ceil(N/nranks) rounded up to a multiple of 4 (default rank 0 of 1 = all rows).  Must be called
- * before daisy_formfactors_build. */
+ * rows_per_rank = ceil(N/nranks) rounded up to a multiple of 256 when nranks > 1 (a 256-column TMA tile of the
+ * residual never straddles two blocks), of 4 when nranks == 1 (default rank 0 of 1 = all rows).  Callers must not
+ * re-derive the layout: daisy_ctx_row_range returns it.  Must be called before daisy_formfactors_alloc / _build /
+ * _write_rows (DAISY_E_STATE afterwards: the allocation and any IPC mapping are sized from the row range). */
 int daisy_ctx_set_partition(daisy_ctx *ctx, int rank, int nranks);
 int daisy_ctx_row_range(daisy_ctx *ctx, int *row0, int *row1, int *rows_per_rank);
 /* optional: run kernels on this cudaStream_t (default: the legacy default stream) */
@@ -68,6 +70,18 @@ int daisy_ctx_set_stream(daisy_ctx *ctx, void *cuda_stream);
 int daisy_query_closest(daisy_ctx *ctx, int n, const float *rays6, daisy_hit *hits);
 /* same with device pointers (no copies) */
 int daisy_query_closest_device(daisy_ctx *ctx, int n, const float *d_rays6, daisy_hit *d_hits);
+
+/* ---- camera ray cast + shading (the step right after the solve; the only other optixQuery consumer) ---------------
+ * replaces OptixPrimeFunctionality::traceScreen(Drawer::RenderContext)                 VS/OptixPrimeFunctionality.cpp:83-131
+ *      with triangle_math::isFacingBack (VS/triangle_math.cpp:76-86) and Drawer::interpolate (VS/Drawer.cpp:161-186)
+ * fused behind the closest-hit traversal.  rays6: width*height*samples rays in the order Camera::gen_rays_for_screen
+ * emits them ((y*width + x)*samples + s, VS/Camera.h:54-80; "direction" = the un-projected far-plane point, exactly as
+ * the reference passes it); eye3 = camera.eye; patch_rgb = N x 3, get_color_of_patch of every patch (interpolate = 1,
+ * radiosityRendering) or the material rgbcolor of every patch (interpolate = 0).  out_rgb = optixView, height*width*3,
+ * clamped to [0,1].  hits_out (may be NULL) = the width*height*samples hit records, for callers that rebuild
+ * trianglesonScreen for picking. */
+int daisy_trace_screen(daisy_ctx *ctx, int width, int height, int samples, const float *rays6, const float *eye3,
+                       const float *patch_rgb, int interpolate, float *out_rgb, daisy_hit *hits_out);
 
 /* ---- form factors -----------------------------------------------------------------------------------------
  * replaces parallellism::runCalculateRadiosityMatrix(SimpleMesh&)                    VS/parallellism.cu:4-89
@@ -90,6 +104,9 @@ int daisy_formfactors_write_rows(daisy_ctx *ctx, int row0, int nrows, const floa
 /* parity aid: visibility hit masks of rows [row0,row0+nrows): out[(r-row0)*N + c], bit i = sample i of the pair
  * (min(r,c) -> max(r,c)) saw its destination (the test at VS/OptixPrimeFunctionality.cpp:208); 0 if not traced. */
 int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int nrows, uint64_t *out);
+/* parity aid for matrices too large to read back: exact, order-free digests of rows [row0,row0+nrows) of the resident
+ * matrix -- xor_out[r] = XOR over columns c of the float bit patterns, wsum_out[r] = SUM of bits * (2c+1) mod 2^64 */
+int daisy_formfactors_row_digest(daisy_ctx *ctx, int row0, int nrows, uint32_t *xor_out, uint64_t *wsum_out);
 /* what the last daisy_formfactors_build did: mutually facing pairs this context traced, how many of those have
  * their lower patch index inside this context's row range (summing that over all ranks counts every pair of the
  * matrix once), rays cast (= pairs_traced * S), and device milliseconds of the LBVH build and of the fused

@@ -303,10 +303,18 @@ static inline int ray_box(const float o[3], const float inv[3], const float lo[3
     return tn <= tf * 1.00001f + 1e-30f;
 }
 
+/* tie bookkeeping for the parity report: tie_t = the largest-so-far t at which two DIFFERENT triangles were accepted with
+ * exactly equal t while that t was the running minimum; the ray's closest hit is a tie iff tie_t == best.t at the end */
+static inline void hit_update_tie(orc_hit *best, float *tie_t, float t, int id, float u, float v) {
+    if (tie_t && best->triangleId >= 0 && t == best->t && id != best->triangleId) *tie_t = t;
+    hit_update(best, t, id, u, v);
+}
+
 /* seed >= 0: test that triangle first (pure optimisation: the (t,id) minimum is order independent) */
-static void closest_one(const orc_mesh *m, const orc_bvh *bv, const float *r, int seed, orc_hit *out) {
+static void closest_one_tie(const orc_mesh *m, const orc_bvh *bv, const float *r, int seed, orc_hit *out, int *tie) {
     wray w; wray_setup(r, &w);
     orc_hit best = { -1.0f, -1, 0.0f, 0.0f };
+    float tie_store = -1.0f, *tie_t = tie ? &tie_store : NULL;
     if (seed >= 0) {
         v3 a, b, c; tri_verts(m, seed, &a, &b, &c);
         float t, u, v;
@@ -324,7 +332,7 @@ static void closest_one(const orc_mesh *m, const orc_bvh *bv, const float *r, in
                 for (int i = nd->first; i < nd->first + nd->count; i++) {
                     int k = bv->order[i]; v3 a, b, c; tri_verts(m, k, &a, &b, &c);
                     float t, u, v;
-                    if (wray_tri(&w, a, b, c, &t, &u, &v)) hit_update(&best, t, k, u, v);
+                    if (k != seed && wray_tri(&w, a, b, c, &t, &u, &v)) hit_update_tie(&best, tie_t, t, k, u, v);
                 }
             } else {
                 float tl, tr;
@@ -339,6 +347,36 @@ static void closest_one(const orc_mesh *m, const orc_bvh *bv, const float *r, in
         }
     }
     *out = best;
+    if (tie) *tie = (best.triangleId >= 0 && tie_store == best.t) ? 1 : 0;
+}
+static void closest_one(const orc_mesh *m, const orc_bvh *bv, const float *r, int seed, orc_hit *out) {
+    closest_one_tie(m, bv, r, seed, out, NULL);
+}
+
+/* Parity report: over the visibility rays of the listed rows (pairs traced exactly as orc_radmat_rows traces them, direct
+ * variant), how many have a closest hit whose t is shared bit for bit by two different triangles -- the cases where the
+ * (t, id) tie rule, not geometry, decides the mask bit.  OptiX Prime's own tie-breaking is unpinned (closed source). */
+int64_t orc_count_ties(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, const int *rows, int nrows, int variant, int nthreads) {
+    int N = m->ntri;
+    int64_t ties = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : ties)
+    for (int ri = 0; ri < nrows; ri++)
+        for (int c = 0; c < N; c++) {
+            const int r = rows[ri];
+            if (c == r) continue;
+            int lo = r < c ? r : c, hi = r < c ? c : r;
+            if (!(orc_p2p_ff(m, lo, hi, variant) > 0.0f)) continue;
+            for (int i = 0; i < S; i++) {
+                float ray[6]; orc_pair_ray(m, lo, hi, uv[2 * i], uv[2 * i + 1], ray);
+                orc_hit h; int tie = 0;
+                closest_one_tie(m, b, ray, hi, &h, &tie);
+                ties += tie;
+            }
+        }
+    return ties;
 }
 
 void orc_query_closest(const orc_mesh *m, const orc_bvh *b, int n, const float *rays6, orc_hit *hits) {
@@ -367,6 +405,50 @@ static uint64_t pair_mask(const orc_mesh *m, const orc_bvh *b, const float *uv, 
     return mask;
 }
 
+/* one row r of RadMat (and its masks) into F_row / mask_row (each N entries, either may be NULL); returns rays cast */
+static int64_t radmat_one_row(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, int r, int variant, int reciprocity, int brute,
+                              float *F_row, uint64_t *mask_row) {
+    int N = m->ntri;
+    int64_t rays = 0;
+    for (int c = 0; c < N; c++) {
+        float val = 0.0f; uint64_t mask = 0;
+        if (c != r) {
+            int lo = r < c ? r : c, hi = r < c ? c : r;
+            if (!reciprocity) {
+                /* tripletlist[row*N+col].m_value > 0 with row<col                          :190 */
+                float ff_lohi = orc_p2p_ff(m, lo, hi, variant);
+                if (ff_lohi > 0.0f) {
+                    mask = pair_mask(m, b, uv, S, lo, hi, brute); rays += S;
+                    float visibility = 0;
+                    for (int i = 0; i < S; i++) visibility += ((mask >> i) & 1) ? 1.0f : 0.0f;
+                    visibility = visibility / S;                                         /* :211 */
+                    if (visibility > 0) {
+                        float ff_rc = (r == lo) ? ff_lohi : orc_p2p_ff(m, r, c, variant);
+                        ff_rc = (ff_rc > 0.0) ? ff_rc : 0.0f;                            /* parallellism.cu:101-107 */
+                        /* Tripl(row,col, visibility*m_value): float*double -> double; setFromTriplets casts to float */
+                        val = (float)((double)visibility * (double)ff_rc);
+                    }
+                }
+            } else {
+                /* calculateRadiosityMatrix: p2pFormfactor(row,col) = formfactor*visibility (float), host pi */
+                float ff = orc_p2p_ff(m, lo, hi, ORC_FF_HOST);
+                mask = pair_mask(m, b, uv, S, lo, hi, brute); rays += S;
+                float visibility = 0;
+                for (int i = 0; i < S; i++) visibility += ((mask >> i) & 1) ? 1.0f : 0.0f;
+                visibility = visibility / S;
+                float ffRC = ff * visibility;
+                if (ffRC > 0.0) {
+                    if (r == lo) val = ffRC;
+                    else val = (orc_surface_tri(m, lo) * ffRC) / orc_surface_tri(m, hi);  /* :343 */
+                }
+            }
+        }
+        if (F_row) F_row[c] = val;
+        if (mask_row) mask_row[c] = mask;
+    }
+    return rays;
+}
+
 int64_t orc_radmat_rows(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, int row0, int row1,
                         int variant, int reciprocity, int brute, float *F_out, uint64_t *masks_out, int nthreads) {
     int N = m->ntri;
@@ -375,45 +457,24 @@ int64_t orc_radmat_rows(const orc_mesh *m, const orc_bvh *b, const float *uv, in
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #endif
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : rays)
-    for (int r = row0; r < row1; r++) {
-        for (int c = 0; c < N; c++) {
-            int64_t o = (int64_t)(r - row0) * N + c;
-            float val = 0.0f; uint64_t mask = 0;
-            if (c != r) {
-                int lo = r < c ? r : c, hi = r < c ? c : r;
-                if (!reciprocity) {
-                    /* tripletlist[row*N+col].m_value > 0 with row<col                          :190 */
-                    float ff_lohi = orc_p2p_ff(m, lo, hi, variant);
-                    if (ff_lohi > 0.0f) {
-                        mask = pair_mask(m, b, uv, S, lo, hi, brute); rays += S;
-                        float visibility = 0;
-                        for (int i = 0; i < S; i++) visibility += ((mask >> i) & 1) ? 1.0f : 0.0f;
-                        visibility = visibility / S;                                         /* :211 */
-                        if (visibility > 0) {
-                            float ff_rc = (r == lo) ? ff_lohi : orc_p2p_ff(m, r, c, variant);
-                            ff_rc = (ff_rc > 0.0) ? ff_rc : 0.0f;                            /* parallellism.cu:101-107 */
-                            /* Tripl(row,col, visibility*m_value): float*double -> double; setFromTriplets casts to float */
-                            val = (float)((double)visibility * (double)ff_rc);
-                        }
-                    }
-                } else {
-                    /* calculateRadiosityMatrix: p2pFormfactor(row,col) = formfactor*visibility (float), host pi */
-                    float ff = orc_p2p_ff(m, lo, hi, ORC_FF_HOST);
-                    mask = pair_mask(m, b, uv, S, lo, hi, brute); rays += S;
-                    float visibility = 0;
-                    for (int i = 0; i < S; i++) visibility += ((mask >> i) & 1) ? 1.0f : 0.0f;
-                    visibility = visibility / S;
-                    float ffRC = ff * visibility;
-                    if (ffRC > 0.0) {
-                        if (r == lo) val = ffRC;
-                        else val = (orc_surface_tri(m, lo) * ffRC) / orc_surface_tri(m, hi);  /* :343 */
-                    }
-                }
-            }
-            if (F_out) F_out[o] = val;
-            if (masks_out) masks_out[o] = mask;
-        }
-    }
+    for (int r = row0; r < row1; r++)
+        rays += radmat_one_row(m, b, uv, S, r, variant, reciprocity, brute, F_out ? F_out + (int64_t)(r - row0) * N : NULL,
+                               masks_out ? masks_out + (int64_t)(r - row0) * N : NULL);
+    return rays;
+}
+
+/* the same for an arbitrary list of rows (sampled-row parity checks and the bounded CPU baseline sample) */
+int64_t orc_radmat_rowlist(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, const int *rows, int nrows,
+                           int variant, int reciprocity, int brute, float *F_out, uint64_t *masks_out, int nthreads) {
+    int N = m->ntri;
+    int64_t rays = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) reduction(+ : rays)
+    for (int i = 0; i < nrows; i++)
+        rays += radmat_one_row(m, b, uv, S, rows[i], variant, reciprocity, brute, F_out ? F_out + (int64_t)i * N : NULL,
+                               masks_out ? masks_out + (int64_t)i * N : NULL);
     return rays;
 }
 

@@ -74,6 +74,12 @@ int64_t orc_radmat_rows(const orc_mesh *m, const orc_bvh *b, const float *uv, in
                         int variant, int reciprocity, int brute, float *F_out, uint64_t *masks_out,
                         int nthreads);
 
+int64_t orc_radmat_rowlist(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, const int *rows, int nrows,
+                           int variant, int reciprocity, int brute, float *F_out, uint64_t *masks_out, int nthreads);
+
+/* rays of the listed rows whose closest hit distance is shared bit for bit by two different triangles (parity report) */
+int64_t orc_count_ties(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, const int *rows, int nrows, int variant, int nthreads);
+
 /* upper-triangle form (c > r only): F_rc = RadMat(r,c), F_cr = RadMat(c,r), masks; direct variant */
 int64_t orc_radmat_upper(const orc_mesh *m, const orc_bvh *b, const float *uv, int S, int row0, int row1,
                          int variant, float *F_rc, float *F_cr, uint64_t *masks_out, int nthreads);

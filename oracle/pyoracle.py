@@ -56,6 +56,11 @@ def lib():
         L.orc_radmat_rows.restype = C.c_int64
         L.orc_radmat_rows.argtypes = [C.POINTER(_Mesh), C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, fp, C.POINTER(C.c_uint64), C.c_int]
+        L.orc_radmat_rowlist.restype = C.c_int64
+        L.orc_radmat_rowlist.argtypes = [C.POINTER(_Mesh), C.c_void_p, fp, C.c_int, ip, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, fp, C.POINTER(C.c_uint64), C.c_int]
+        L.orc_count_ties.restype = C.c_int64
+        L.orc_count_ties.argtypes = [C.POINTER(_Mesh), C.c_void_p, fp, C.c_int, ip, C.c_int, C.c_int, C.c_int]
         L.orc_radmat_upper.restype = C.c_int64
         L.orc_radmat_upper.argtypes = [C.POINTER(_Mesh), C.c_void_p, fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, fp,
                                        C.POINTER(C.c_uint64), C.c_int]
@@ -138,6 +143,24 @@ class Oracle:
                                       int(reciprocity), int(brute), _fp(F),
                                       masks.ctypes.data_as(C.POINTER(C.c_uint64)) if want_masks else None, nthreads)
         return F, masks, int(rays)
+
+    def radmat_rowlist(self, uv, rows, variant=0, reciprocity=False, brute=False, want_masks=True, nthreads=0):
+        """radmat_rows for an arbitrary list of rows (one host thread per row)."""
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        rows = np.ascontiguousarray(rows, np.int32)
+        F = np.empty((rows.size, self.N), np.float32)
+        masks = np.empty((rows.size, self.N), np.uint64) if want_masks else None
+        rays = self.L.orc_radmat_rowlist(C.byref(self.mesh), self.bvh, _fp(uv), uv.shape[0], rows.ctypes.data_as(C.POINTER(C.c_int)),
+                                         rows.size, variant, int(reciprocity), int(brute), _fp(F),
+                                         masks.ctypes.data_as(C.POINTER(C.c_uint64)) if want_masks else None, nthreads)
+        return F, masks, int(rays)
+
+    def count_ties(self, uv, rows, variant=0, nthreads=0):
+        """Visibility rays of the listed rows whose closest-hit distance is shared exactly by two different triangles."""
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        rows = np.ascontiguousarray(rows, np.int32)
+        return int(self.L.orc_count_ties(C.byref(self.mesh), self.bvh, _fp(uv), uv.shape[0], rows.ctypes.data_as(C.POINTER(C.c_int)),
+                                         rows.size, variant, nthreads))
 
     def radmat_upper(self, uv, row0, row1, variant=0, nthreads=0):
         uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
