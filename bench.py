@@ -43,6 +43,17 @@ WORKLOADS = {
 FIXTURE_SCENES = ("cornellbox_blacklight", "colorballs")
 
 
+def parity_rows(N):
+    """The constant set of 16 matrix rows that stand for the whole matrix wherever the CPU oracle is involved (parity block,
+    cpu_baseline sample, --impl reference): first / last rows, 64-row tile boundaries, the row-block boundaries of 2/4/8-GPU
+    partitions and a few fixed pseudo-random rows."""
+    rows = {0, 1, 63, 64, N // 2 - 1, N // 2, N - 64, N - 1, N // 8, 3 * (N // 8), 5 * (N // 8), 7 * (N // 8) - 1}
+    rng = np.random.RandomState(12345)
+    while len(rows) < 16:
+        rows.add(int(rng.randint(0, N)))
+    return np.array(sorted(rows), np.int32)
+
+
 def wavelengths_for(K):
     if K == 9:
         return np.arange(200, 601, 50).astype(np.float32)  # reference main.cpp:94
@@ -112,35 +123,33 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_reference_run(sc, wl, K, budget_s, steps, coeff_dir, log=lambda *a: None):
-    """The reference's CPU path on the host cores, on a bounded row sample of the workload.
+    """The reference's CPU path on the host cores, on the constant row sample `parity_rows` of the workload.
 
-    form factors + visibility: the oracle's restatement of calculateAllVisibility (OptiX Prime itself is closed source),
-    all host threads; gather: the reference's UNMODIFIED Lightning.h + vendored Eigen 3.2.10 compiled into
-    oracle/_ref (single-threaded, as in the reference), fed the sampled rows; full-pass time = SpMV time scaled by
-    N/rows + the measured per-patch loop."""
+    form factors + visibility: the oracle's restatement of calculateAllVisibility (OptiX Prime itself is closed source) on
+    an explicit number of OpenMP threads (all host cores, whatever OMP_NUM_THREADS the launcher exported); gather: the
+    reference's UNMODIFIED Lightning.h + vendored Eigen 3.2.10 compiled into oracle/_ref (single-threaded, as in the
+    reference), fed the sampled rows; full-pass time = SpMV time scaled by N/rows + the measured per-patch loop.
+    The rows are processed in a fixed order, one batch of `threads` rows at a time; if the time budget runs out the
+    remaining batches are dropped (the sample string says how many rows were done)."""
     from daisyriot_b200 import scenes
     from oracle import pyoracle, pyref
     N = sc.numtriangles
     uv = scenes.msvc_sample_pattern(1)
     orc = pyoracle.Oracle.from_scene(sc)
-    cores = pyoracle.num_procs()
+    cores = max(1, pyoracle.num_procs())
     orc.bvh
-    # --- FF + visibility rays/s on sampled row batches spread over the scene, sized to the time budget;
-    # the oracle's row loop runs one row per host thread
+    rows = parity_rows(N)
     rows_done, rays_done, t_ff, Fs = [], 0, 0.0, []
-    batch = max(1, cores)
-    starts = list(range(0, max(1, N - batch + 1), max(batch, N // 64)))
-    np.random.RandomState(7).shuffle(starts)
-    for s0 in starts:
-        if t_ff >= budget_s or len(rows_done) >= 1024:
+    for b0 in range(0, len(rows), cores):
+        if rows_done and t_ff >= budget_s:
             break
-        s1 = min(N, s0 + batch)
+        batch = rows[b0:b0 + cores]
         t0 = time.time()
-        F_b, _, rays = orc.radmat_rows(uv, s0, s1, want_masks=False)
+        F_b, _, rays = orc.radmat_rowlist(uv, batch, want_masks=False, nthreads=cores)
         t_ff += time.time() - t0
         rays_done += rays
-        rows_done += list(range(s0, s1))
-        Fs += [F_b[i] for i in range(s1 - s0)]
+        rows_done += [int(r) for r in batch]
+        Fs += [F_b[i] for i in range(len(batch))]
     rays_per_s = rays_done / t_ff if t_ff > 0 else 0.0
     log(f"cpu ff: {len(rows_done)} rows, {rays_done} rays in {t_ff:.1f}s on {cores} threads")
     out = {"ff_rays_per_s": rays_per_s, "ff_rows": len(rows_done), "ff_rays": rays_done, "ff_seconds": t_ff, "cores_ff": cores,
@@ -181,6 +190,13 @@ def cpu_reference_run(sc, wl, K, budget_s, steps, coeff_dir, log=lambda *a: None
     return out
 
 
+def bench_config(name, N, K, S, world):
+    """The `config` object, identical in both arms (the driver compares them key by key)."""
+    nloc = -(-N // world)
+    return {"workload": name, "patches": N, "bands": K, "rays_per_pair": int(S), "parallelism": f"rowshard{world}",
+            "cache": "F rows per GPU %.2f GB > 126 MB L2 (inputs larger than L2, no flush needed)" % (4.0 * nloc * N / 1e9)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -189,20 +205,197 @@ def run_reference(args):
     sc, wl, E, M, tmp = make_workload(name)
     N, K, _ = WORKLOADS[name]
     t0 = time.time()
-    r = cpu_reference_run(sc, wl, K, budget_s=args.cpu_budget * max(1, args.steps) / 5.0, steps=args.steps + args.warmup, coeff_dir=tmp,
+    r = cpu_reference_run(sc, wl, K, budget_s=min(60.0, 3.0 * args.cpu_budget), steps=args.steps + args.warmup, coeff_dir=tmp,
                           log=lambda *a: print(*a, file=sys.stderr))
     val = r["it_per_s"]
     line = {"impl": "reference", "metric": "radiosity_gather_iterations_per_s", "value": val, "unit": "iterations/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": (1e3 / val) if val else None, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "patches": N, "bands": K, "rays_per_pair": 50},
+            "config": bench_config(name, N, K, 50, args.gpus),
             "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": 1, "kind": r["gather_kind"],
-                             "sample": f"Lightning.h+Eigen pass on {r['ff_rows']} of {N} matrix rows ({r.get('gather_sample_nnz')} nnz), SpMV time scaled by N/rows"},
+                             "sample": f"Lightning.h+Eigen pass on {r['ff_rows']} fixed rows of {N} ({r.get('gather_sample_nnz')} nnz), SpMV time scaled by N/rows"},
             "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "formfactor": {"metric": "formfactor_visibility_rays_per_s", "value": r["ff_rays_per_s"], "unit": "rays/s", "cores": r["cores_ff"],
-                           "kind": "port", "sample": f"{r['ff_rows']} rows, {r['ff_rays']} rays in {r['ff_seconds']:.1f} s"},
+                           "kind": "port", "threads": r["cores_ff"], "sample": f"{r['ff_rows']} fixed rows, {r['ff_rays']} rays in {r['ff_seconds']:.1f} s"},
             "wall_s": time.time() - t0}
     print(json.dumps(line))
+
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def parity_block(optixP, solver, sc, uv, E, M, K, world, rank, torch, name, stop_threshold=200.0):
+    """Parity evidence reported with the numbers: the constant row sample `parity_rows` of the matrix the
+    bench just built, against the CPU oracle (rank 0 computes the oracle rows once, every rank compares the rows it owns):
+
+    * mask_mismatches / F_bit_mismatches: visibility masks and matrix entries that differ (bit-exact bar => 0);
+    * ties: rays of those rows whose closest-hit distance is shared bit for bit by two different triangles, i.e. where the
+      (t, triangle id) tie rule and not geometry decides (OptiX Prime's own rule is unpinned);
+    * digest: every row of the resident matrix against the committed per-row digests of this workload
+      (tests/golden/rowdigest_<workload>.npz, exact integer digests) -- proves that 1, 2, 4 and 8 GPUs build the same matrix;
+    * gather: the whole solve is repeated with the residual vector read back after every pass; for the sampled rows each new
+      residual entry is recomputed in FP64 from the ORACLE's matrix row and the device's previous residual vector
+      (Lightning.h:196-226), B is accumulated alongside; max_rel_* are true relative errors over entries above 1e-6 of
+      the band's largest value; passes / passes_from_host_sums apply the reference's stop rule to the device's band sums and
+      to FP64 sums of the read-back residuals."""
+    import torch.distributed as tdist
+    from daisyriot_b200 import _lib, api
+    N = sc.numtriangles
+    rows = parity_rows(N)
+    r0, r1 = optixP.row_range
+    t0 = time.time()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    F_ref = np.zeros((len(rows), N), np.float32)
+    m_ref = np.zeros((len(rows), N), np.uint64)
+    ties = rays = 0
+    if rank == 0:
+        from oracle import pyoracle
+        orc = pyoracle.Oracle.from_scene(sc)
+        nth = max(1, pyoracle.num_procs())
+        F_ref, m_ref, rays = orc.radmat_rowlist(uv, rows, nthreads=nth)
+        ties = orc.count_ties(uv, rows, nthreads=nth)
+    if world > 1:
+        tF = torch.from_numpy(F_ref).to(dev); tm = torch.from_numpy(m_ref.view(np.int64)).to(dev)
+        tdist.broadcast(tF, 0); tdist.broadcast(tm, 0)
+        F_ref = tF.cpu().numpy(); m_ref = tm.cpu().numpy().view(np.uint64)
+    oracle_s = time.time() - t0
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
+        return float(t.item())
+
+    def allmaxf(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    mine = [i for i, r in enumerate(rows) if r0 <= r < r1]
+    rm = api.RadMat(optixP)
+    f_mis = m_mis = 0
+    for i in mine:
+        r = int(rows[i])
+        f_mis += int(np.count_nonzero(rm.rows(r, 1)[0].view(np.uint32) != F_ref[i].view(np.uint32)))
+        m_mis += int(np.count_nonzero(optixP.visibilityMasks(r, 1)[0] != m_ref[i]))
+    out = {"rows": [int(r) for r in rows], "rows_checked": int(allsum(len(mine))), "rays_checked": int(rays),
+           "mask_mismatches": int(allsum(m_mis)), "F_bit_mismatches": int(allsum(f_mis)), "max_rel_F": 0.0, "ties": int(ties),
+           "oracle_seconds": oracle_s}
+    if out["F_bit_mismatches"]:
+        out["max_rel_F"] = None
+    # ---- committed per-row digests of the whole matrix
+    dpath = os.path.join(ROOT, "tests", "golden", f"rowdigest_{name}.npz")
+    if os.path.exists(dpath) and r1 > r0:
+        g = np.load(dpath)
+        dx, dw = rm.row_digest()
+        bad = int(np.count_nonzero((dx != g["xor"][r0:r1]) | (dw != g["wsum"][r0:r1])))
+        out["digest"] = {"file": os.path.relpath(dpath, ROOT), "rows_checked": int(allsum(r1 - r0)), "row_mismatches": int(allsum(bad))}
+    elif os.path.exists(dpath):
+        out["digest"] = {"file": os.path.relpath(dpath, ROOT), "rows_checked": int(allsum(0)), "row_mismatches": int(allsum(0))}
+    else:
+        out["digest"] = None
+    # ---- the solve, pass by pass, on the sampled rows
+    solver.reset()
+    nloc = r1 - r0
+    mat = sc.mat_idx
+    Mr = {i: M.astype(np.float64)[mat[int(rows[i])]] for i in mine}          # column-major: M[m][j, i] = M(i, j)
+    Bchk = {i: E[:, int(rows[i])].astype(np.float64) for i in mine}
+    res_prev = np.ascontiguousarray(E, np.float32)
+    sums = res_prev.astype(np.float64).sum(1)
+    host_sums = sums.copy()
+    passes = host_passes = 0
+    host_done = False
+    max_rel_res = max_rel_B = 0.0
+    FLOOR = 1e-6
+    while sums.sum() > stop_threshold and passes < 2000:
+        sums = solver.step(True)
+        passes += 1
+        Bl, Rl = solver.read_local()
+        if world > 1:
+            parts = [torch.zeros((K, optixP_rows_per_rank(optixP)), dtype=torch.float32, device=dev) for _ in range(world)]
+            mineT = torch.zeros((K, optixP_rows_per_rank(optixP)), dtype=torch.float32, device=dev)
+            mineT[:, :nloc] = torch.from_numpy(Rl).to(dev)
+            tdist.all_gather(parts, mineT)
+            res_new = torch.cat(parts, 1)[:, :N].cpu().numpy()
+        else:
+            res_new = Rl
+        if not host_done:
+            if host_sums.sum() > stop_threshold:
+                host_passes += 1
+                host_sums = res_new.astype(np.float64).sum(1)
+            if not (host_sums.sum() > stop_threshold):
+                host_done = True
+        band_max = np.abs(res_new).max(1).astype(np.float64) + 1e-300
+        for i in mine:
+            r = int(rows[i])
+            want = Mr[i].T @ (res_prev.astype(np.float64) @ F_ref[i].astype(np.float64))   # M_p (F[r,:] . residual_k)_k
+            got = Rl[:, r - r0].astype(np.float64)
+            Bchk[i] = Bchk[i] + want
+            big = np.abs(want) > FLOOR * band_max
+            if big.any():
+                max_rel_res = max(max_rel_res, float((np.abs(got - want)[big] / np.abs(want)[big]).max()))
+            gotB = Bl[:, r - r0].astype(np.float64)
+            bigB = np.abs(Bchk[i]) > 0
+            if bigB.any():
+                max_rel_B = max(max_rel_B, float((np.abs(gotB - Bchk[i])[bigB] / np.abs(Bchk[i])[bigB]).max()))
+        res_prev = res_new
+    out["gather"] = {"passes": int(passes), "passes_from_host_sums": int(host_passes), "max_rel_residual": allmaxf(max_rel_res),
+                     "max_rel_B": allmaxf(max_rel_B), "tolerance": 1e-5, "floor": "1e-6 of the band's largest entry",
+                     "rows": "the sampled rows; FP64 products of the oracle's matrix rows with the device's residual vectors"}
+    out["max_rel_B"] = out["gather"]["max_rel_B"]
+    out["passes"] = int(passes)
+    out["seconds"] = time.time() - t0
+    return out
+
+
+def incumbent_block(dz, uv):
+    """The one GPU kernel the reference already has -- parallellism::runCalculateRadiosityMatrix / calculateRow
+    (parallellism.cu:4-111), compiled UNMODIFIED for sm_100a into oracle/_ref -- against this library's counterpart
+    (daisy_unoccluded_rows) on the same scenes.  Both deliver the dense N x N list of 16-byte triplets in host memory, which
+    is what the reference's entry point returns; seconds are wall clock around the whole call (the reference's managed-memory
+    chunks and host copies included, ours with its device-to-host copies included)."""
+    from daisyriot_b200 import scenes
+    from oracle import pyref
+    if not pyref.cuda_kernel_available(False):
+        return {"unavailable": "oracle/_ref/libdaisy_ref_cuda.so not built (needs /root/reference at build time)"}
+    out = {"kernel": "parallellism::calculateRow (reference, recompiled for sm_100a)", "ours": "k_unoccluded via daisy_unoccluded_rows", "cases": []}
+    cases = [("cornellbox_blacklight", scenes.load_scene_npz(os.path.join(ROOT, "tests", "golden", "cornellbox_blacklight.npz"))),
+             ("cornell_16k", scenes.cornell_box(16384))]
+    for nm, sc in cases:
+        N = sc.numtriangles
+        p = dz.OptixPrimeFunctionality(dz.MeshS.from_scene(sc), rands=uv)
+        p.runCalculateRadiosityMatrix(0, min(N, 256), 0)  # warm-up (module load, allocation)
+        t0 = time.time()
+        ours = p.runCalculateRadiosityMatrix(0, N, 0)["m_value"]
+        t_ours = time.time() - t0
+        pyref.cuda_run_calculate_radiosity_matrix(sc.vertices, sc.normals, sc.tri[:64])  # warm-up on a 64-patch slice
+        ref, t_ref = pyref.cuda_run_calculate_radiosity_matrix(sc.vertices, sc.normals, sc.tri)
+        nz = ours > 0
+        same_support = bool(((ref > 0) == nz).all())
+        rel = float((np.abs(ours - ref)[nz] / ours[nz]).max()) if nz.any() else 0.0
+        out["cases"].append({"scene": nm, "patches": int(N), "reference_seconds": t_ref, "ours_seconds": t_ours, "speedup": t_ref / t_ours,
+                             "pairs_per_s_reference": N * N / t_ref, "pairs_per_s_ours": N * N / t_ours,
+                             "same_facing_pairs": same_support, "max_rel_diff": rel})
+        p.close()
+        del ours, ref
+    return out
+
+
+
+def peaks_sm_mhz():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("sm_max_mhz", 1965.0))
+    except Exception:
+        return 1965.0
+
+
+def optixP_rows_per_rank(optixP):
+    from daisyriot_b200 import _lib
+    n = C.c_int()
+    _lib.check(_lib.lib().daisy_ctx_row_range(optixP._ctx, None, None, C.byref(n)))
+    return n.value
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -248,6 +441,9 @@ def run_ours(args):
 
     # ---- form-factor stage (timed once; it is seconds long, so self-warming): host mesh -> LBVH -> fused FF/visibility
     barrier()
+    ff_sampler = ClockSampler(local)
+    if rank == 0:
+        ff_sampler.start()
     t0 = time.time()
     mesh = dz.MeshS.from_scene(sc)
     optixP = dz.OptixPrimeFunctionality(mesh, device=local, rands=uv, rank=rank, nranks=world)
@@ -257,6 +453,7 @@ def run_ours(args):
         optixP.cudaCalculateRadiosityMatrix()
     torch.cuda.synchronize()
     ff_wall = allmax(time.time() - t0)
+    ff_clocks = ff_sampler.stop() if rank == 0 else None
     st = optixP.stats()
     ff_ms = allmax(st["ff_ms"])
     lbvh_ms = allmax(st["lbvh_ms"])
@@ -313,15 +510,33 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     # measured DRAM bytes per launch of the gather kernel (one ncu --set full capture per workload, profiles/gather_traffic.json)
-    ff_ncu = None
+    # form-factor stage roofline: instruction issue.  The warp-instruction count of k_ff_tiles is a property of the workload
+    # (same tiles, same candidate lists whatever the schedule), taken from the committed ncu capture of THIS workload
+    # (profiles/ff_ncu.json, keyed by workload); the kernel time and the SM clock are measured in this run.
+    ff_ncu = ff_roof = None
     try:
-        ff_ncu = json.load(open(os.path.join(ROOT, "profiles", "ff_ncu.json")))
+        ff_ncu = json.load(open(os.path.join(ROOT, "profiles", "ff_ncu.json"))).get(name)
     except Exception:
         pass
+    if ff_ncu and ff_ncu.get("warp_instructions"):
+        clk = ((ff_clocks or {}).get("sm_mhz") or peaks_sm_mhz()) * 1e6
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        wi = float(ff_ncu["warp_instructions"])  # whole matrix; with N ranks every rank issues 1/N of it (tiles are hashed over the ranks)
+        ach = wi / world / (ff_ms * 1e-3)
+        pk = sms * 4 * clk
+        ff_roof = {"bound": "issue", "achieved": ach, "peak": pk, "unit": "warp-instructions/s per GPU", "frac": ach / pk,
+                   "warp_instructions": wi, "warp_instructions_per_ray": wi / max(rays, 1.0), "sm_clock_mhz": clk / 1e6,
+                   "threads_per_warp_instruction": ff_ncu.get("threads_active_per_warp_instruction"),
+                   "source": ff_ncu.get("source"), "peak_note": "SMs x 4 schedulers x SM clock sampled during the build"}
+    elif ff_ncu is None:
+        ff_roof = {"unavailable": f"no ncu capture of k_ff_tiles for workload {name} under profiles/ff_ncu.json"}
+    # measured DRAM bytes per launch of the gather kernel (one ncu capture per workload and GPU count, profiles/gather_traffic.json;
+    # the N-GPU entries were captured on one GPU holding rank 0's row block of an N-way partition: same kernel, same rows x columns)
     traffic = None
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json"))).get(name)
-        if t and world == 1:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "gather_traffic.json")))
+        t = tj.get(name if world == 1 else f"{name}@{world}")
+        if t:
             traffic = t["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -380,6 +595,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     conv_s = allmax(time.time() - t0)
 
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_block(optixP, solver, sc, uv, E, M, K, world, rank, torch, name)
+        except Exception as ex:
+            if world > 1:
+                raise  # a rank that drops out of the collectives would hang the others
+            parity = {"failed": repr(ex)}
+    incumbent = None
+    if world == 1 and rank == 0 and not args.no_incumbent:
+        try:
+            incumbent = incumbent_block(dz, uv)
+        except Exception as ex:
+            incumbent = {"unavailable": repr(ex)}
+
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
@@ -396,8 +626,7 @@ def run_ours(args):
             "metric": "radiosity_gather_iterations_per_s", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "reference example scene (tests/golden fixture)" if name in FIXTURE_SCENES else "synthetic",
-            "config": {"workload": name, "patches": N, "bands": K, "rays_per_pair": int(uv.shape[0]), "parallelism": f"rowshard{world}",
-                       "cache": "F rows per GPU %.2f GB > 126 MB L2 (inputs larger than L2, no flush needed)" % (4.0 * nloc * N / 1e9)},
+            "config": bench_config(name, N, K, uv.shape[0], world),
             "e2e": e2e, "gpu_launches": int((2 + (1 if K > 9 else 0) + (1 if world > 1 and not args.no_fused else 0)) * args.steps),
             "clocks": clocks,
             "roofline": {"kernel": ("k_gather_mma" if K > 9 else "k_gather_tma") + "+k_gather_epilogue", "bound": "hbm", "achieved": achieved,
@@ -409,7 +638,9 @@ def run_ours(args):
                            "pairs_facing": int(pairs_unique), "pairs_traced_all_ranks": int(pairs_traced), "rays": int(rays), "kernel_ms": ff_ms,
                            "lbvh_build_ms": lbvh_ms, "e2e_wall_s": ff_wall,
                            "e2e_rays_per_s": rays / ff_wall,
-                           "ncu": ff_ncu},  # pipe / cache utilisation of the traversal kernel from the committed ncu capture
+                           "roofline": ff_roof, "clocks": ff_clocks,
+                           "ncu": ff_ncu},  # pipe / cache utilisation of the traversal kernel from the committed ncu capture of this workload
+            "parity": parity, "incumbent": incumbent,
             "converge": {"rule": "sum of residual over bands and patches <= 200 (Lightning.h:145-151)", "passes": int(conv_passes),
                          "seconds": conv_s, "total_with_formfactors_s": conv_s + ff_wall},
         }
@@ -429,6 +660,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DAISY_WORKLOAD", "cornell_128k"), choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU form-factor sampling for the baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the sampled rows")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the timing of the reference's own calculateRow kernel")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-gather per pass instead of the epilogue kernel's peer stores")
     ap.add_argument("--no-peer-tiles", action="store_true", help="multi-GPU: trace every tile touching this rank's rows instead of exchanging mirrored tiles")
     args = ap.parse_args()

@@ -30,9 +30,178 @@ static void free_ctx(daisy_ctx *c) {
     if (c->peers_set)
         for (int g = 0; g < c->nranks && g < 16; g++)
             if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
-    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane); cudaFree(c->d_pid);
+    cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane); cudaFree(c->d_pid); cudaFree(c->d_nbr);
     cudaFree(c->d_nodes); cudaFree(c->d_F); cudaFree(c->d_order); free(c->h_order); cudaFree(c->d_vadj_off); cudaFree(c->d_vadj);
     delete c;
+}
+
+
+// ---- plane ids ---------------------------------------------------------------------------------------------------------
+// pid[t] >= 1: id of a plane that holds triangle t together with at least one other triangle; 0: none.  Two triangles with
+// the same id lie in one plane in the sense coplanar skipping needs (formfactor.cu, k_tri_planes): every vertex of every
+// member is within PLANE_TAU x scene extent of ONE plane P, and every member's own normal is within 1e-3 of P's.
+//  * axis-aligned planes are recognised exactly (all three vertices carry the very same x, y or z);
+//  * other planes (rotated boxes, ramps) are found by seeded fitting in double precision: triangles are bucketed by their
+//    rounded plane equation, the largest unassigned triangle of a bucket seeds a plane, members within tolerance are
+//    collected, the plane is refitted to the members' vertices (least squares) and members are collected again -- the
+//    refits matter because the normal of one small triangle with float-rounded vertices is only good to ~1e-5 rad.
+// Whatever ends up alone keeps id 0 and is simply never skipped.
+#define PLANE_TAU 3e-7
+namespace {
+struct V3d { double x, y, z; };
+inline V3d vsub(V3d a, V3d b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+inline double vdot(V3d a, V3d b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3d vcross(V3d a, V3d b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+
+// least-squares plane through a point set: centroid + eigenvector of the smallest eigenvalue of the covariance (Jacobi)
+bool fit_plane(const std::vector<V3d> &pts, V3d &n, V3d &c) {
+    if (pts.size() < 3) return false;
+    c = { 0, 0, 0 };
+    for (const V3d &p : pts) { c.x += p.x; c.y += p.y; c.z += p.z; }
+    c.x /= pts.size(); c.y /= pts.size(); c.z /= pts.size();
+    double a[3][3] = { { 0 } }, v[3][3] = { { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } };
+    for (const V3d &p : pts) {
+        const double d[3] = { p.x - c.x, p.y - c.y, p.z - c.z };
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) a[i][j] += d[i] * d[j];
+    }
+    for (int sweep = 0; sweep < 32; sweep++) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (fabs(a[p][q]) < 1e-300) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < 3; k++) { const double akp = a[k][p], akq = a[k][q]; a[k][p] = cs * akp - sn * akq; a[k][q] = sn * akp + cs * akq; }
+                for (int k = 0; k < 3; k++) { const double apk = a[p][k], aqk = a[q][k]; a[p][k] = cs * apk - sn * aqk; a[q][k] = sn * apk + cs * aqk; }
+                for (int k = 0; k < 3; k++) { const double vkp = v[k][p], vkq = v[k][q]; v[k][p] = cs * vkp - sn * vkq; v[k][q] = sn * vkp + cs * vkq; }
+            }
+    }
+    int m = 0;
+    if (a[1][1] < a[m][m]) m = 1;
+    if (a[2][2] < a[m][m]) m = 2;
+    n = { v[0][m], v[1][m], v[2][m] };
+    const double l = sqrt(vdot(n, n));
+    if (!(l > 0)) return false;
+    n = { n.x / l, n.y / l, n.z / l };
+    return true;
+}
+} // namespace
+
+static void assign_plane_ids(const float *vertices, const int32_t *tri_idx, int ntri, float ext, std::vector<int> &pid) {
+    pid.assign((size_t)(ntri > 0 ? ntri : 1), 0);
+    int next_id = 1;
+    auto vert = [&](int t, int k) -> V3d {
+        const float *p = vertices + 3 * (size_t)tri_idx[6 * (size_t)t + k];
+        return { (double)p[0], (double)p[1], (double)p[2] };
+    };
+    // (1) exact axis-aligned planes
+    std::unordered_map<uint64_t, int> ids;
+    for (int i = 0; i < ntri; i++) {
+        const float *a = vertices + 3 * (size_t)tri_idx[6 * (size_t)i], *b = vertices + 3 * (size_t)tri_idx[6 * (size_t)i + 1],
+                    *cc = vertices + 3 * (size_t)tri_idx[6 * (size_t)i + 2];
+        int axis = -1, count = 0;
+        for (int d = 0; d < 3; d++)
+            if (a[d] == b[d] && a[d] == cc[d]) { axis = d; count++; }
+        if (count != 1) continue; // not axis-aligned, or degenerate (a segment or a point)
+        float v = a[axis] + 0.0f; // -0 -> +0
+        uint32_t bits;
+        memcpy(&bits, &v, 4);
+        const uint64_t key = ((uint64_t)axis << 32) | bits;
+        auto it = ids.find(key);
+        if (it == ids.end()) it = ids.emplace(key, next_id++).first;
+        pid[(size_t)i] = it->second;
+    }
+    // (2) general planes among the rest
+    if (!(ext > 0.f)) return;
+    const double tau = PLANE_TAU * (double)ext;
+    struct TP { V3d n; double d, area2; };
+    std::vector<TP> tp((size_t)ntri);
+    std::unordered_map<uint64_t, std::vector<int>> buckets;
+    const double qn = 2e-3, qd = 2e-3 * (double)ext;
+    for (int i = 0; i < ntri; i++) {
+        if (pid[(size_t)i]) continue;
+        const V3d a = vert(i, 0), b = vert(i, 1), c = vert(i, 2);
+        V3d n = vcross(vsub(b, a), vsub(c, a));
+        const double l = sqrt(vdot(n, n));
+        tp[(size_t)i].area2 = l;
+        if (!(l > 0)) continue;
+        n = { n.x / l, n.y / l, n.z / l };
+        // canonical sign: the component of largest magnitude is positive (a plane has two unit normals)
+        const double ax = fabs(n.x), ay = fabs(n.y), az = fabs(n.z);
+        const double lead = (ax >= ay && ax >= az) ? n.x : (ay >= az ? n.y : n.z);
+        if (lead < 0) n = { -n.x, -n.y, -n.z };
+        tp[(size_t)i].n = n;
+        tp[(size_t)i].d = vdot(n, a);
+        const int64_t k0 = (int64_t)floor(n.x / qn), k1 = (int64_t)floor(n.y / qn), k2 = (int64_t)floor(n.z / qn), k3 = (int64_t)floor(tp[(size_t)i].d / qd);
+        const uint64_t key = ((uint64_t)(k0 & 0xffff) << 48) | ((uint64_t)(k1 & 0xffff) << 32) | ((uint64_t)(k2 & 0xffff) << 16) | (uint64_t)(k3 & 0xffff);
+        buckets[key].push_back(i);
+    }
+    std::vector<V3d> pts;
+    std::vector<int> members, rest;
+    std::vector<char> taken((size_t)ntri, 0);
+    for (auto &kv : buckets) {
+        rest = kv.second;
+        for (int round = 0; round < 8 && rest.size() >= 2; round++) {
+            int seed = rest[0];
+            for (int t : rest)
+                if (tp[(size_t)t].area2 > tp[(size_t)seed].area2) seed = t;
+            V3d n = tp[(size_t)seed].n, c0 = vert(seed, 0);
+            auto collect = [&]() {
+                members.clear();
+                for (int t : rest) {
+                    if (fabs(vdot(n, tp[(size_t)t].n)) < 1.0 - 5e-7) continue; // own normal within 1e-3 rad of the plane's
+                    double dist = 0.0;
+                    for (int k = 0; k < 3; k++) dist = fmax(dist, fabs(vdot(n, vsub(vert(t, k), c0))));
+                    if (dist <= tau) members.push_back(t);
+                }
+            };
+            collect();
+            for (int refit = 0; refit < 3 && members.size() >= 2; refit++) {
+                pts.clear();
+                for (int t : members)
+                    for (int k = 0; k < 3; k++) pts.push_back(vert(t, k));
+                V3d nn, cc;
+                if (!fit_plane(pts, nn, cc)) break;
+                n = nn; c0 = cc;
+                const size_t before = members.size();
+                collect();
+                if (members.size() == before && refit > 0) break;
+            }
+            bool has_seed = false;
+            for (int t : members) has_seed |= (t == seed);
+            if (members.size() >= 2 && has_seed) {
+                const int id = next_id++;
+                for (int t : members) pid[(size_t)t] = id;
+            } else {
+                members.assign(1, seed); // the seed stays alone (id 0); take it out and try the next largest
+            }
+            for (int t : members) taken[(size_t)t] = 1;
+            std::vector<int> keep;
+            for (int t : rest)
+                if (!taken[(size_t)t]) keep.push_back(t);
+            rest.swap(keep);
+        }
+    }
+}
+
+extern "C" int daisy_plane_ids(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int32_t *pid_out) {
+    DZ_REQUIRE(ntri >= 0 && nv >= 0 && (ntri == 0 || (vertices && tri_idx && pid_out)), DAISY_E_INVALID, "daisy_plane_ids: bad argument");
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int i = 0; i < ntri; i++)
+        for (int k = 0; k < 3; k++) {
+            const int v = tri_idx[6 * (size_t)i + k];
+            DZ_REQUIRE(v >= 0 && v < nv, DAISY_E_INVALID, "daisy_plane_ids: triangle index out of range");
+            for (int d = 0; d < 3; d++) { lo[d] = fminf(lo[d], vertices[3 * (size_t)v + d]); hi[d] = fmaxf(hi[d], vertices[3 * (size_t)v + d]); }
+        }
+    float ext = 0.f;
+    for (int d = 0; d < 3; d++) if (ntri) ext = fmaxf(ext, hi[d] - lo[d]);
+    std::vector<int> pid;
+    assign_plane_ids(vertices, tri_idx, ntri, ext, pid);
+    for (int i = 0; i < ntri; i++) pid_out[i] = pid[(size_t)i];
+    return DAISY_OK;
 }
 
 static void set_partition(daisy_ctx *c, int rank, int nranks) {
@@ -88,29 +257,13 @@ extern "C" int daisy_ctx_create(const float *vertices, int nv, const float *norm
     CC(cudaMalloc(&c->d_tri, sizeof(int) * 6 * (size_t)(ntri > 0 ? ntri : 1)));
     CC(cudaMalloc(&c->d_geom, sizeof(PatchGeom) * (size_t)(ntri > 0 ? ntri : 1)));
     CC(cudaMalloc(&c->d_plane, sizeof(float4) * (size_t)(ntri > 0 ? ntri : 1)));
+    CC(cudaMalloc(&c->d_nbr, sizeof(int) * 32 * (size_t)(ntri > 0 ? ntri : 1)));
     if (nv) CC(cudaMemcpy(c->d_vertices, vertices, sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice));
     if (nn) CC(cudaMemcpy(c->d_normals, normals, sizeof(float) * 3 * (size_t)nn, cudaMemcpyHostToDevice));
     if (ntri) CC(cudaMemcpy(c->d_tri, tri_idx, sizeof(int) * 6 * (size_t)ntri, cudaMemcpyHostToDevice));
     {
-        // exact axis-aligned plane ids: triangles whose three vertices carry the very same x (or y, or z) share an id.  Lets the
-        // form-factor kernel recognise "coplanar with this patch" for walls, floors and the like by an integer compare.
-        std::vector<int> pid((size_t)(ntri > 0 ? ntri : 1), 0);
-        std::unordered_map<uint64_t, int> ids;
-        for (int i = 0; i < ntri; i++) {
-            const float *a = vertices + 3 * (size_t)tri_idx[6 * (size_t)i], *b = vertices + 3 * (size_t)tri_idx[6 * (size_t)i + 1],
-                        *cc = vertices + 3 * (size_t)tri_idx[6 * (size_t)i + 2];
-            int axis = -1, count = 0;
-            for (int d = 0; d < 3; d++)
-                if (a[d] == b[d] && a[d] == cc[d]) { axis = d; count++; }
-            if (count != 1) continue; // not axis-aligned, or degenerate (a segment or a point)
-            float v = a[axis] + 0.0f; // -0 -> +0
-            uint32_t bits;
-            memcpy(&bits, &v, 4);
-            const uint64_t key = ((uint64_t)axis << 32) | bits;
-            auto it = ids.find(key);
-            if (it == ids.end()) it = ids.emplace(key, (int)ids.size() + 1).first;
-            pid[(size_t)i] = it->second;
-        }
+        std::vector<int> pid;
+        assign_plane_ids(vertices, tri_idx, ntri, ext, pid);
         CC(cudaMalloc(&c->d_pid, sizeof(int) * pid.size()));
         CC(cudaMemcpy(c->d_pid, pid.data(), sizeof(int) * pid.size(), cudaMemcpyHostToDevice));
     }

@@ -130,7 +130,7 @@ __global__ void k_hierarchy(const uint64_t *__restrict__ keys, int N, int2 *__re
 // bottom-up refit: the second thread to arrive at a node merges its two children and moves on
 __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__restrict__ tv, int N, float pad,
                         const int2 *__restrict__ children, const int *__restrict__ parent, float *__restrict__ box /* (2N-1) x 6 */,
-                        int *__restrict__ flags, float4 *__restrict__ tribox) {
+                        int *__restrict__ flags, float4 *__restrict__ tribox, const int *__restrict__ pid, int *__restrict__ spid /* 2N-1 */) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     int tri = (int)(uint32_t)keys[p];
@@ -141,6 +141,7 @@ __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__res
     lo[2] = fminf(t.a.z, fminf(t.b.z, t.c.z)) - pad; hi[2] = fmaxf(t.a.z, fmaxf(t.b.z, t.c.z)) + pad;
     size_t self = (size_t)(N - 1) + p;
     for (int d = 0; d < 3; d++) { box[self * 6 + d] = lo[d]; box[self * 6 + 3 + d] = hi[d]; }
+    spid[self] = pid[tri]; // subtree plane id: the id shared by every triangle below a node, 0 if they differ (or have none)
     tribox[2 * (size_t)tri] = make_float4(lo[0], lo[1], lo[2], 0.f);
     tribox[2 * (size_t)tri + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
     if (N == 1) return;
@@ -157,13 +158,18 @@ __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__res
             box[(size_t)node * 6 + d] = fminf(vb[l * 6 + d], vb[r * 6 + d]);
             box[(size_t)node * 6 + 3 + d] = fmaxf(vb[l * 6 + 3 + d], vb[r * 6 + 3 + d]);
         }
+        {
+            volatile int *vs = spid;
+            const int sl = vs[l], sr = vs[r];
+            spid[node] = (sl == sr) ? sl : 0;
+        }
         __threadfence();
         node = parent[node];
     }
 }
 
 __global__ void k_pack_nodes(const uint64_t *__restrict__ keys, int N, const int2 *__restrict__ children,
-                             const float *__restrict__ box, const int *__restrict__ pid, BvhNode *__restrict__ nodes) {
+                             const float *__restrict__ box, const int *__restrict__ spid, BvhNode *__restrict__ nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N - 1) return;
     int2 ch = children[i];
@@ -177,7 +183,7 @@ __global__ void k_pack_nodes(const uint64_t *__restrict__ keys, int N, const int
     // leaves refer to the ORIGINAL triangle id
     int li = ch.x >= 0 ? ch.x : ~(int)(uint32_t)keys[~ch.x];
     int ri = ch.y >= 0 ? ch.y : ~(int)(uint32_t)keys[~ch.y];
-    n.d = make_int4(li, ri, li < 0 ? pid[~li] : 0, ri < 0 ? pid[~ri] : 0);
+    n.d = make_int4(li, ri, spid[l], spid[r]); // plane id common to everything below each child (leaf: the triangle's own), 0 = mixed
     nodes[i] = n;
 }
 
@@ -209,6 +215,8 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     int2 *d_children = nullptr;
     int *d_parent = nullptr, *d_flags = nullptr;
     float *d_box = nullptr;
+    int *d_spid = nullptr;
+    DZ_CUDA(cudaMalloc(&d_spid, sizeof(int) * (size_t)(2 * N)));
     DZ_CUDA(cudaMalloc(&d_keys, sizeof(uint64_t) * (size_t)npad));
     DZ_CUDA(cudaMalloc(&d_children, sizeof(int2) * (size_t)N));
     DZ_CUDA(cudaMalloc(&d_parent, sizeof(int) * (size_t)(2 * N)));
@@ -224,9 +232,9 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     if (N > 1) {
         k_hierarchy<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_parent);
     }
-    k_refit<<<(N + 255) / 256, 256, 0, st>>>(d_keys, ctx->d_triverts, N, ctx->pad, d_children, d_parent, d_box, d_flags, ctx->d_tribox);
+    k_refit<<<(N + 255) / 256, 256, 0, st>>>(d_keys, ctx->d_triverts, N, ctx->pad, d_children, d_parent, d_box, d_flags, ctx->d_tribox, ctx->d_pid, d_spid);
     if (N > 1) {
-        k_pack_nodes<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_box, ctx->d_pid, ctx->d_nodes);
+        k_pack_nodes<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_box, d_spid, ctx->d_nodes);
         ctx->root = 0;
     } else {
         ctx->root = ~0; // single triangle: the root is the leaf of triangle 0
@@ -244,7 +252,7 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     ctx->lbvh_ms = ms;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(d_keys); cudaFree(d_children); cudaFree(d_parent); cudaFree(d_flags); cudaFree(d_box);
+    cudaFree(d_keys); cudaFree(d_children); cudaFree(d_parent); cudaFree(d_flags); cudaFree(d_box); cudaFree(d_spid);
     return DAISY_OK;
 }
 

@@ -165,7 +165,7 @@ struct __align__(16) BvhNode {
     float4 a; // L.lo.x L.lo.y L.lo.z L.hi.x
     float4 b; // L.hi.y L.hi.z R.lo.x R.lo.y
     float4 c; // R.lo.z R.hi.x R.hi.y R.hi.z
-    int4 d;   // left, right, plane id of the left child if it is a leaf (else 0), same for the right child
+    int4 d;   // left, right, plane id shared by every triangle below the left child (0 = mixed / none), same for the right child
 };
 
 // conservative slab test against [0, tmax]; boxes are padded at build time, fminf/fmaxf drop the NaN of 0*inf
@@ -218,7 +218,8 @@ struct daisy_ctx {
                                 // (Morton order of the LBVH build => 64 consecutive slots are spatially compact); -1 = empty slot
     int *h_order = nullptr;     // host copy (job lists of row-restricted runs)
     int nslots = 0;             // slots = ceil(N / 64) * 64
-    int *d_pid = nullptr;       // per triangle: id (>= 1) of the axis-aligned plane all three vertices lie in EXACTLY, 0 if none
+    int *d_pid = nullptr;       // per triangle: plane id (>= 1; api.cu assign_plane_ids), 0 if it shares its plane with no other triangle
+    int *d_nbr = nullptr;       // per triangle: its neighbours in that plane, 32 ints ([0] = count), formfactor.cu k_tri_planes
     float4 *d_plane = nullptr;  // per triangle: unit geometric normal, w = smallest altitude if coplanar skipping is safe for it, else -1
     float ext = 0.f;            // largest scene extent
     // LBVH

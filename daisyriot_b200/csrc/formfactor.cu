@@ -16,7 +16,11 @@
 #include <vector>
 
 #define TILE 64
+#define NBR_CAP 32 // ints per triangle in the neighbour table: [0] = count, then up to 31 triangles of its own plane
 #define FF_THREADS 256
+#ifndef FF_MINBLOCKS
+#define FF_MINBLOCKS 3
+#endif
 #define PI_D 3.14159265358979323846
 #define PI_F 3.14159265358979323846f
 
@@ -123,10 +127,14 @@ __device__ bool tri_overlap_2d(const d3 *P, const d3 *Q, d3 o, d3 ux, d3 uy, dou
 }
 
 __global__ void k_tri_planes(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox, const BvhNode *__restrict__ nodes, int root,
-                             int N, double tau, double tau2, float4 *__restrict__ plane) {
+                             int N, double tau, double tau2, float grow, const int *__restrict__ pid, float4 *__restrict__ plane, int *__restrict__ nbr) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N) return;
     const TriVerts T = tv[t];
+    const int my_pid = pid[t];
+    int n_nbr = 0;
+    int *my_nbr = nbr + (size_t)t * NBR_CAP;
+    my_nbr[0] = 0;
     const d3 P[3] = { dv(T.a), dv(T.b), dv(T.c) };
     const d3 e1 = dsub(P[1], P[0]), e2 = dsub(P[2], P[0]), e3 = dsub(P[2], P[1]);
     d3 n = dcross(e1, e2);
@@ -139,7 +147,8 @@ __global__ void k_tri_planes(const TriVerts *__restrict__ tv, const float4 *__re
     const double l1 = sqrt(ddot(e1, e1));
     const d3 ux = { e1.x / l1, e1.y / l1, e1.z / l1 };
     const d3 uy = dcross(n, ux);
-    const float4 b0 = tribox[2 * (size_t)t], b1 = tribox[2 * (size_t)t + 1];
+    float4 b0 = tribox[2 * (size_t)t], b1 = tribox[2 * (size_t)t + 1];
+    b0.x -= grow; b0.y -= grow; b0.z -= grow; b1.x += grow; b1.y += grow; b1.z += grow;
     int stack[64];
     int sp = 0, cur = root;
     while (safe) {
@@ -150,7 +159,12 @@ __global__ void k_tri_planes(const TriVerts *__restrict__ tv, const float4 *__re
                 const d3 Q[3] = { dv(K.a), dv(K.b), dv(K.c) };
                 double dist = 0.0;
                 for (int j = 0; j < 3; j++) dist = fmax(dist, fabs(ddot(n, dsub(Q[j], P[0]))));
-                if (dist <= 4.0 * tau) { // coplanar neighbour
+                const bool same_plane = my_pid != 0 && pid[k] == my_pid;
+                if (same_plane) { // goes on this patch's neighbour list: the only triangles of its plane its edge samples have to test
+                    if (n_nbr == NBR_CAP - 1) safe = false;
+                    else my_nbr[1 + n_nbr++] = k;
+                }
+                if (dist <= 4.0 * tau || same_plane) { // coplanar neighbour
                     const d3 f1 = dsub(Q[1], Q[0]), f2 = dsub(Q[2], Q[0]), f3 = dsub(Q[2], Q[1]);
                     const d3 nk = dcross(f1, f2);
                     const double A2k = sqrt(ddot(nk, nk));
@@ -174,7 +188,8 @@ __global__ void k_tri_planes(const TriVerts *__restrict__ tv, const float4 *__re
             cur = stack[--sp];
         }
     }
-    plane[t] = make_float4((float)n.x, (float)n.y, (float)n.z, safe ? (float)h : -1.f);
+    plane[t] = make_float4((float)n.x, (float)n.y, (float)n.z, (safe && my_pid != 0) ? (float)h : -1.f);
+    my_nbr[0] = safe ? n_nbr : 0;
 }
 
 #define COPLANAR_TAU 3e-7f // x scene extent: a triangle within this distance of a patch's plane counts as coplanar
@@ -184,7 +199,8 @@ int dz_precompute_geom(daisy_ctx *ctx) {
     k_patch_geom<<<(ctx->N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_vertices, ctx->d_normals, ctx->d_tri, ctx->N, ctx->d_geom);
     DZ_CUDA(cudaGetLastError());
     k_tri_planes<<<(ctx->N + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_triverts, ctx->d_tribox, ctx->d_nodes, ctx->root, ctx->N,
-                                                             (double)COPLANAR_TAU * ctx->ext, (double)OVERLAP_TAU * ctx->ext, ctx->d_plane);
+                                                             (double)COPLANAR_TAU * ctx->ext, (double)OVERLAP_TAU * ctx->ext, 2.0f * ctx->pad, ctx->d_pid,
+                                                             ctx->d_plane, ctx->d_nbr);
     DZ_CUDA(cudaGetLastError());
     return DAISY_OK;
 }
@@ -322,8 +338,7 @@ __device__ __noinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const T
 // direction between the two centroids.  Skipping any axis only makes the test say "may intersect" more often, so the
 // candidate list is always a superset of the triangles any of the S rays can touch; rays are then tested against the
 // list with the very same watertight routine and the same (t, id) rule => identical masks, far fewer node visits.
-#define FF_QCAP 6 // pending watertight tests per lane
-#define HEAVY_CAP 1024 // deferred per-ray-walk pairs per tile; beyond that they are resolved on the spot
+#define FF_QCAP 6 // pending watertight tests per lane (4 bits each in one register)
 #define SHAFT_CAP 256 // ints of global scratch per pair slot; longer lists fall back to per-ray LBVH walks
 struct Shaft {
     float lox, loy, loz, hix, hiy, hiz; // hull AABB
@@ -377,57 +392,36 @@ __device__ __forceinline__ bool shaft_box(const Shaft &s, float lox, float loy, 
     return true;
 }
 
-// Premise of coplanar skipping for one side of a pair (see k_tri_planes): unit normal n and a point a of the patch's
-// plane; on = the patch qualifies and every ray of the pair meets the plane steeply enough.
-struct RingSide { float nx, ny, nz, ax, ay, az; bool on; int pid; }; // pid: exact axis-aligned plane id of the patch (0 = none)
-
-// true if all three vertices of T lie within tau of the plane (n, a)
-__device__ __forceinline__ bool tri_in_plane(const RingSide &r, const TriVerts &T, float tau) {
-    const float d0 = r.nx * (T.a.x - r.ax) + r.ny * (T.a.y - r.ay) + r.nz * (T.a.z - r.az);
-    const float d1 = r.nx * (T.b.x - r.ax) + r.ny * (T.b.y - r.ay) + r.nz * (T.b.z - r.az);
-    const float d2 = r.nx * (T.c.x - r.ax) + r.ny * (T.c.y - r.ay) + r.nz * (T.c.z - r.az);
-    return fmaxf(fabsf(d0), fmaxf(fabsf(d1), fabsf(d2))) <= tau;
-}
-// cheap pre-test with the leaf's padded box: can the plane pass through it at all?
-__device__ __forceinline__ bool box_meets_plane(const RingSide &r, float lox, float loy, float loz, float hix, float hiy, float hiz) {
-    const float cx = 0.5f * (lox + hix) - r.ax, cy = 0.5f * (loy + hiy) - r.ay, cz = 0.5f * (loz + hiz) - r.az;
-    const float rad = 0.5f * ((hix - lox) * fabsf(r.nx) + (hiy - loy) * fabsf(r.ny) + (hiz - loz) * fabsf(r.nz));
-    return fabsf(r.nx * cx + r.ny * cy + r.nz * cz) <= rad;
-}
-
-// collect the triangles (other than lo and hi) whose leaf box meets the shaft.  Triangles coplanar with lo (or hi) when
-// that side's premise holds go to the RING list, stored downwards from the end of the slot: only the edge samples have to
-// test them.  Everything else goes to the MAIN list at the start of the slot.  Returns n_main | n_ring << 16, or -1 if the
-// two lists do not fit SHAFT_CAP.
-__device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root, const Shaft &sh,
-                                                const RingSide &rl, const RingSide &rh, float tau, int lo, int hi, int *__restrict__ cand) {
-    int n_main = 0, n_ring = 0;
+// collect the triangles (other than lo and hi) whose leaf box meets the shaft into the pair's candidate list.  skip_lo /
+// skip_hi: plane id of lo / hi when that side's premise of coplanar skipping holds (see k_tri_planes and the kernel), else 0.
+// Triangles lying in such a plane are left out altogether -- the only ones a ray of this pair can touch are the patch's
+// direct neighbours, which the edge samples test from the precomputed neighbour lists -- and, since every LBVH node
+// carries the plane id common to all triangles below it, whole subtrees of a wall the pair starts or ends on are never
+// entered.  Returns the number of candidates, or -1 if they do not fit SHAFT_CAP.
+__device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, int root, const Shaft &sh, int skip_lo, int skip_hi, int lo, int hi,
+                                                int *__restrict__ cand) {
+    int n_main = 0;
     int stack[64];
     int sp = 0;
     int cur = root;
     bool overflow = false;
-    auto leaf = [&](int k, int kp, float lox, float loy, float loz, float hix, float hiy, float hiz) {
-        if (k == lo || k == hi) return;
-        if (n_main + n_ring == SHAFT_CAP) { overflow = true; return; }
-        // exact plane ids decide without looking at the geometry whenever both the candidate and the patch have one:
-        // equal ids = all six vertices share one coordinate exactly; different ids = different axis-aligned planes
-        bool ring = (rl.on && kp != 0 && kp == rl.pid) || (rh.on && kp != 0 && kp == rh.pid);
-        const bool tl = !ring && rl.on && (kp == 0 || rl.pid == 0) && box_meets_plane(rl, lox, loy, loz, hix, hiy, hiz);
-        const bool th = !ring && rh.on && (kp == 0 || rh.pid == 0) && box_meets_plane(rh, lox, loy, loz, hix, hiy, hiz);
-        if (tl || th) {
-            const TriVerts T = tv[k];
-            ring = (tl && tri_in_plane(rl, T, tau)) || (th && tri_in_plane(rh, T, tau));
-        }
-        if (ring) cand[SHAFT_CAP - 1 - n_ring++] = k;
-        else cand[n_main++] = k;
-    };
     if (cur < 0) return 0; // single-triangle hierarchy: no third triangle exists
     while (!overflow) {
-        BvhNode nd = nodes[cur];
-        bool hl = shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
-        bool hr = shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
-        if (hl && nd.d.x < 0) { leaf(~nd.d.x, nd.d.z, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y); hl = false; }
-        if (hr && nd.d.y < 0) { leaf(~nd.d.y, nd.d.w, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w); hr = false; }
+        const BvhNode nd = nodes[cur];
+        const bool sl = nd.d.z != 0 && (nd.d.z == skip_lo || nd.d.z == skip_hi);
+        const bool sr = nd.d.w != 0 && (nd.d.w == skip_lo || nd.d.w == skip_hi);
+        bool hl = !sl && shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
+        bool hr = !sr && shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
+        if (hl && nd.d.x < 0) {
+            const int k = ~nd.d.x;
+            if (k != lo && k != hi) { if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
+            hl = false;
+        }
+        if (hr && nd.d.y < 0) {
+            const int k = ~nd.d.y;
+            if (k != lo && k != hi) { if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
+            hr = false;
+        }
         if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
         else if (hl) cur = nd.d.x;
         else if (hr) cur = nd.d.y;
@@ -436,7 +430,7 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
             cur = stack[--sp];
         }
     }
-    return overflow ? -1 : (n_main | (n_ring << 16));
+    return overflow ? -1 : n_main;
 }
 
 // Visibility mask of one pair with the whole warp: lane = sample (device order), a candidate list is walked in lock step
@@ -446,8 +440,8 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
 // sample, the ring list (coplanar with lo or hi, see shaft_candidates) only by the edge samples.
 __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox,
                                                    const TriVerts &Tlo, const TriVerts &Thi, int hi, const int *cand,
-                                                   int n_main, int n_ring, int n_inner, float m_req, const float *s_uv, const unsigned char *s_perm, int S,
-                                                   int lane, int *wq, int *wk, float4 *wb) {
+                                                   int n_main, const int *nbr_lo, const int *nbr_hi, int n_inner, float m_req, const float *s_uv,
+                                                   const unsigned char *s_perm, int S, int lane, int *wk, float4 *wb) {
     unsigned mask_lo = 0, mask_hi = 0;
     for (int pass = 0; pass * 32 < S; pass++) {
         const int i = pass * 32 + lane;
@@ -471,6 +465,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         // triangle.  The expensive watertight tests are then issued for whole queues at a time, so a warp instruction
         // slot is spent on them only when many lanes have one pending, not whenever a single lane does.
         int qlen = 0;
+        unsigned qreg = 0; // queued candidates: 4-bit positions inside the staged chunk of 16
         auto flush = [&]() {
 #ifdef DAISY_FF_STATS
             {
@@ -484,12 +479,13 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 if (lane == 0) atomicAdd(&g_ffstats[22], 1ull);
 #endif
                 if (alive && t < qlen) {
-                    const int k = wq[t * 32 + lane];
+                    const int k = wk[(qreg >> (4 * t)) & 15];
                     TriVerts tr = tv[k];
                     if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) alive = false;
                 }
             }
             qlen = 0;
+            qreg = 0;
         };
 #ifdef DAISY_FF_STATS
         int dbg_iters = 0;
@@ -514,7 +510,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                         const int j = j0 + jj;
                         if (j < nb) {
                             const float4 b0 = wb[2 * j], b1 = wb[2 * j + 1];
-                            if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { wq[qlen * 32 + lane] = wk[j]; qlen++; }
+                            if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { qreg |= (unsigned)j << (4 * qlen); qlen++; }
                         }
                     }
 #ifdef DAISY_FF_STATS
@@ -526,35 +522,42 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 }
             }
         }
-        // Ring list (coplanar with lo or hi): only samples closer to an edge of their triangles than the pair's required
-        // margin have to test it.  They are few (usually 1-6 of 50), so the roles flip: the edge sample's ray is broadcast
-        // and lane = ring candidate.
-        if (n_ring > 0 && pass * 32 + 31 >= n_inner) {
+        // Neighbour lists (triangles in the plane of lo / hi next to the patch, null if that side's premise does not hold):
+        // only samples closer to an edge of their triangles than the pair's required margin have to test them.  They are few
+        // (usually 0-3 of 50), so the roles flip: the edge sample's ray is broadcast and lane = neighbour.
+        if ((nbr_lo || nbr_hi) && pass * 32 + 31 >= n_inner) {
             const float mg = fminf(fminf(u, v), 1.0f - u - v);
             unsigned edge = __ballot_sync(0xffffffffu, alive && i >= n_inner && mg < m_req);
-            while (edge) {
-                const int e = __ffs(edge) - 1;
-                edge &= edge - 1;
-                WRay we;
-                we.o.x = __shfl_sync(0xffffffffu, w.o.x, e); we.o.y = __shfl_sync(0xffffffffu, w.o.y, e); we.o.z = __shfl_sync(0xffffffffu, w.o.z, e);
-                we.perm = __shfl_sync(0xffffffffu, w.perm, e); we.kx = we.ky = we.kz = 0; // the select-based test reads perm only
-                we.Sx = __shfl_sync(0xffffffffu, w.Sx, e); we.Sy = __shfl_sync(0xffffffffu, w.Sy, e); we.Sz = __shfl_sync(0xffffffffu, w.Sz, e);
-                const f3 inve = mk3(__shfl_sync(0xffffffffu, inv.x, e), __shfl_sync(0xffffffffu, inv.y, e), __shfl_sync(0xffffffffu, inv.z, e));
-                const f3 oie = mk3(__shfl_sync(0xffffffffu, oi.x, e), __shfl_sync(0xffffffffu, oi.y, e), __shfl_sync(0xffffffffu, oi.z, e));
-                const float thie = __shfl_sync(0xffffffffu, thi, e);
-                bool hit = false;
-                for (int c0 = 0; c0 < n_ring; c0 += 32) {
-                    if (c0 + lane < n_ring) {
-                        const int k = __ldcg(cand + SHAFT_CAP - 1 - (c0 + lane));
-                        const float4 b0 = tribox[2 * (size_t)k], b1 = tribox[2 * (size_t)k + 1];
-                        if (ray_box_fma(oie, inve, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thie)) {
+            if (edge) {
+                // lane < n_lo: neighbour of lo; n_lo <= lane < n_lo + n_hi: neighbour of hi (NBR_CAP - 1 <= 31 each: two rounds at most)
+                const int n_lo = nbr_lo ? __ldg(nbr_lo) : 0, n_hi = nbr_hi ? __ldg(nbr_hi) : 0;
+                for (int c0 = 0; c0 < n_lo + n_hi; c0 += 32) {
+                    const int c = c0 + lane;
+                    int k = -1;
+                    if (c < n_lo) k = __ldg(nbr_lo + 1 + c);
+                    else if (c < n_lo + n_hi) k = __ldg(nbr_hi + 1 + (c - n_lo));
+                    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+                    if (k >= 0) { b0 = tribox[2 * (size_t)k]; b1 = tribox[2 * (size_t)k + 1]; }
+                    unsigned todo = edge;
+                    while (todo) {
+                        const int e = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        WRay we;
+                        we.o.x = __shfl_sync(0xffffffffu, w.o.x, e); we.o.y = __shfl_sync(0xffffffffu, w.o.y, e); we.o.z = __shfl_sync(0xffffffffu, w.o.z, e);
+                        we.perm = __shfl_sync(0xffffffffu, w.perm, e); we.kx = we.ky = we.kz = 0; // the select-based test reads perm only
+                        we.Sx = __shfl_sync(0xffffffffu, w.Sx, e); we.Sy = __shfl_sync(0xffffffffu, w.Sy, e); we.Sz = __shfl_sync(0xffffffffu, w.Sz, e);
+                        const f3 inve = mk3(__shfl_sync(0xffffffffu, inv.x, e), __shfl_sync(0xffffffffu, inv.y, e), __shfl_sync(0xffffffffu, inv.z, e));
+                        const f3 oie = mk3(__shfl_sync(0xffffffffu, oi.x, e), __shfl_sync(0xffffffffu, oi.y, e), __shfl_sync(0xffffffffu, oi.z, e));
+                        const float thie = __shfl_sync(0xffffffffu, thi, e);
+                        bool hit = false;
+                        if (k >= 0 && ray_box_fma(oie, inve, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thie)) {
                             const TriVerts tr = tv[k];
                             float t2, u2, v2;
                             if (wray_tri_sel(we, xyz(tr.a), xyz(tr.b), xyz(tr.c), t2, u2, v2) && (t2 < thie || (t2 == thie && k < hi))) hit = true;
                         }
+                        if (__any_sync(0xffffffffu, hit)) { if (lane == e) alive = false; edge &= ~(1u << e); }
                     }
                 }
-                if (__any_sync(0xffffffffu, hit) && lane == e) alive = false;
             }
         }
 #ifdef DAISY_FF_STATS
@@ -575,9 +578,9 @@ struct FFParams {
     const BvhNode *nodes;
     const float4 *tribox; // padded triangle boxes, 2 float4 per triangle
     const float4 *plane;  // per-triangle plane record (k_tri_planes)
-    const int *pid;       // per-triangle exact axis-aligned plane id (0 = none)
+    const int *pid;       // per-triangle plane id (0 = none)
+    const int *nbr;       // per-triangle neighbour list in its own plane: NBR_CAP ints, [0] = count (k_tri_planes)
     const int *order;     // tile composition: slot -> triangle id (-1 = empty slot); tile T holds slots [64 T, 64 T + 64)
-    float tau;            // coplanarity tolerance
     int n_inner;          // samples [0, n_inner) of the device-order pattern are inner samples
     int ring_on;          // coplanar skipping enabled
     int *scratch;         // gridDim.x * FF_THREADS * SHAFT_CAP candidate slots
@@ -602,19 +605,19 @@ struct FFParams {
 // swap bit: visibility rays always run from the patch with the LOWER triangle id to the one with the higher id
 // (OptixPrimeFunctionality.cpp:186-196, row < col), whatever slots the two occupy.
 #define PAIR_SWAP 0x1000
+#define PAIR_HEAVY 0x2000
 struct FFSmem {
     // phase 1 (sub-patch records of the row / column patches) and phase 2 (per-warp candidate staging) never overlap in
     // time, so they share storage: three CTAs fit one SM
     union {
         struct { PatchGeom g[2 * TILE]; } p1;
         struct {
-            int wq[FF_THREADS / 32][FF_QCAP * 32];
             int wk[FF_THREADS / 32][16];
             float4 wb[FF_THREADS / 32][32];
+            TriVerts tv[2 * TILE]; // vertices of the tile's patches (staged after phase 1)
         } p2;
     } u;
     float area[2 * TILE]; // patch areas (needed after phase 1 by the host-variant reciprocity rule)
-    TriVerts tv[2 * TILE];
     float4 pl[2 * TILE];  // plane records
     int pid[2 * TILE];    // exact plane ids
     int id[2 * TILE];     // triangle ids of the slots, -1 = empty
@@ -622,7 +625,6 @@ struct FFSmem {
     float rc[TILE][TILE + 1]; // F(r->c), indexed [rl][cl]
     float cr[TILE][TILE + 1]; // F(c->r), indexed [cl][rl]
     unsigned short list[TILE * TILE];
-    unsigned short heavy[HEAVY_CAP];
     int nlist, next, job, nown, nheavy, hnext;
     float uv[2 * DAISY_MAX_SAMPLES];
 };
@@ -639,16 +641,15 @@ struct FFSmem {
 #endif
 
 template <int VARIANT>
-__global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
+__global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams P) {
     extern __shared__ __align__(16) unsigned char ff_smem_raw[];
     FFSmem &sm = *reinterpret_cast<FFSmem *>(ff_smem_raw);
     PatchGeom *s_g = sm.u.p1.g;
-    TriVerts *s_tv = sm.tv;
+    TriVerts *s_tv = sm.u.p2.tv;
     float(*s_rc)[TILE + 1] = sm.rc;
     float(*s_cr)[TILE + 1] = sm.cr;
     unsigned short *s_list = sm.list;
     int &s_nlist = sm.nlist, &s_next = sm.next, &s_job = sm.job, &s_nown = sm.nown, &s_nheavy = sm.nheavy, &s_hnext = sm.hnext;
-    unsigned short *s_heavy = sm.heavy;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     if (tid < 2 * DAISY_MAX_SAMPLES) sm.uv[tid] = c_uv[tid];
@@ -682,11 +683,6 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
             const int p = i / 5, q = i - p * 5;
             const int t = max(P.order[(p < TILE ? R0 : C0 - TILE) + p], 0);
             ((float4 *)&s_g[p])[q] = ((const float4 *)&P.geom[t])[q];
-        }
-        for (int i = tid; i < 2 * TILE * 3; i += FF_THREADS) {
-            const int p = i / 3, q = i - p * 3;
-            const int t = max(P.order[(p < TILE ? R0 : C0 - TILE) + p], 0);
-            ((float4 *)&s_tv[p])[q] = ((const float4 *)&P.tv[t])[q];
         }
         __syncthreads();
 
@@ -725,6 +721,14 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
         }
         __syncthreads();
         const int nlist = s_nlist;
+        if (nlist) { // the phase-1 records are dead: their storage now takes the vertices phase 2 works with
+            for (int i = tid; i < 2 * TILE * 3; i += FF_THREADS) {
+                const int p = i / 3, q = i - p * 3;
+                const int t = max(sm.id[p], 0);
+                ((float4 *)&s_tv[p])[q] = ((const float4 *)&P.tv[t])[q];
+            }
+        }
+        __syncthreads();
         if (tid == 0 && nlist) { atomicAdd(P.pair_counter, (unsigned long long)nlist); atomicAdd(P.pair_counter + 1, (unsigned long long)s_nown); }
         FF_CLK(0);
 
@@ -781,9 +785,7 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                 // ~ 8 eps (distance) (its size), against a true value >= (EDGE_MARGIN h)(its edge) cos(theta).  With sizes and
                 // aspect ratios bounded by k_tri_planes that gives cos >= 0.02 on the origin side (distance ~ size) and
                 // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
-                RingSide rl_, rh_;
-                rl_.on = rh_.on = false;
-                rl_.pid = sm.pid[ilo]; rh_.pid = sm.pid[ihi];
+                bool on_lo = false, on_hi = false;
                 if (P.ring_on) {
                     const float4 pl = sm.pl[ilo], ph = sm.pl[ihi];
                     const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
@@ -794,25 +796,18 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                     const float h0 = ph.x * d0x + ph.y * d0y + ph.z * d0z, h1 = ph.x * d1x + ph.y * d1y + ph.z * d1z, h2 = ph.x * d2x + ph.y * d2y + ph.z * d2z;
                     const float lmin = ((l0 > 0.f) == (l1 > 0.f) && (l1 > 0.f) == (l2 > 0.f)) ? fminf(fabsf(l0), fminf(fabsf(l1), fabsf(l2))) : 0.f;
                     const float hmin = ((h0 > 0.f) == (h1 > 0.f) && (h1 > 0.f) == (h2 > 0.f)) ? fminf(fabsf(h0), fminf(fabsf(h1), fabsf(h2))) : 0.f;
-                    rl_.nx = pl.x; rl_.ny = pl.y; rl_.nz = pl.z; rl_.ax = A.a.x; rl_.ay = A.a.y; rl_.az = A.a.z;
-                    rh_.nx = ph.x; rh_.ny = ph.y; rh_.nz = ph.z; rh_.ax = B.a.x; rh_.ay = B.a.y; rh_.az = B.a.z;
                     // required margins (fractions of the altitude): m >= 128 eps D / (h cos), D = 32 h on the origin side
                     const float mlo = (pl.w > 0.f && lmin > 0.f) ? 2.44e-4f * dmax / lmin : 1.f;
                     const float mhi = (ph.w > 0.f && hmin > 0.f) ? 7.63e-6f * (dmax + 64.f * ph.w) * dmax / (hmin * ph.w) : 1.f;
-                    rl_.on = mlo <= EDGE_MARGIN; // inner samples (margin >= EDGE_MARGIN) are then always safe
-                    rh_.on = mhi <= EDGE_MARGIN;
-                    m_req = fmaxf(rl_.on ? mlo : 0.f, rh_.on ? mhi : 0.f);
+                    on_lo = mlo <= EDGE_MARGIN; // inner samples (margin >= EDGE_MARGIN) are then always safe
+                    on_hi = mhi <= EDGE_MARGIN;
+                    m_req = fmaxf(on_lo ? mlo : 0.f, on_hi ? mhi : 0.f);
                 }
-                ncand = shaft_candidates(P.nodes, P.tv, P.root, sh, rl_, rh_, P.tau, sm.id[ilo], sm.id[ihi], my_cand);
-                if (ncand < 0) {
-                    const int h = atomicAdd(&s_nheavy, 1);
-                    if (h < HEAVY_CAP) s_heavy[h] = (unsigned short)idx;
-                    else { // deferral list full (never seen on the benchmark scenes): walk the LBVH per ray right here
-                        uint64_t mask = 0;
-                        for (int i = 0; i < P.S; i++)
-                            if (ray_sees(P.nodes, P.tv, P.root, A, B, sm.id[ilo], sm.id[ihi], c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
-                        finish_pair(rl, cl, mask);
-                    }
+                ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand);
+                if (ncand >= 0) ncand |= (on_lo ? 0x10000 : 0) | (on_hi ? 0x20000 : 0);
+                if (ncand < 0) { // the lists do not fit: flag the pair, phase 2b walks the LBVH per ray
+                    s_list[q] = (unsigned short)(idx | PAIR_HEAVY);
+                    atomicAdd(&s_nheavy, 1);
                 }
             }
             __syncwarp();
@@ -826,14 +821,16 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
                 const int rl = (idj >> 6) & 63, cl = idj & 63;
                 const int ilo = (idj & PAIR_SWAP) ? TILE + cl : rl, ihi = (idj & PAIR_SWAP) ? rl : TILE + cl;
                 const TriVerts Tlo = s_tv[ilo], Thi = s_tv[ihi];
-                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, sm.id[ihi], warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, nc >> 16, P.n_inner, mrq,
-                                               sm.uv, sm.perm, P.S, lane, sm.u.p2.wq[tid >> 5], sm.u.p2.wk[tid >> 5], sm.u.p2.wb[tid >> 5]);
+                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, sm.id[ihi], warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff,
+                                               (nc & 0x10000) ? P.nbr + (size_t)sm.id[ilo] * NBR_CAP : nullptr,
+                                               (nc & 0x20000) ? P.nbr + (size_t)sm.id[ihi] * NBR_CAP : nullptr, P.n_inner, mrq,
+                                               sm.uv, sm.perm, P.S, lane, sm.u.p2.wk[tid >> 5], sm.u.p2.wb[tid >> 5]);
                 if (lane == 0) finish_pair(rl, cl, mask);
 #ifdef DAISY_FF_STATS
                 if (lane == 0) {
                     const int nm = nc & 0xffff, pc = __popcll(mask);
                     const int cat = nm == 0 ? 0 : (pc == 0 ? 1 : (pc == P.S ? 2 : 3)); // simple / occluded / visible / partial
-                    atomicAdd(&g_ffstats[cat], 1ull); atomicAdd(&g_ffstats[4 + cat], (unsigned long long)nm); atomicAdd(&g_ffstats[8 + cat], (unsigned long long)(nc >> 16));
+                    atomicAdd(&g_ffstats[cat], 1ull); atomicAdd(&g_ffstats[4 + cat], (unsigned long long)nm); atomicAdd(&g_ffstats[8 + cat], (unsigned long long)((nc >> 16) & 3));
                     if (nm == 0 && pc == P.S) atomicAdd(&g_ffstats[12], 1ull);
                 }
                 {
@@ -848,23 +845,33 @@ __global__ void __launch_bounds__(FF_THREADS, 3) k_ff_tiles(FFParams P) {
         }
         __syncthreads();
         FF_CLK(4);
-        const int nheavy = min(s_nheavy, HEAVY_CAP);
+        const int nheavy = s_nheavy;
         if (tid == 0 && s_nheavy) atomicAdd(P.pair_counter + 2, (unsigned long long)s_nheavy);
-        while (true) { // 2b
+        // 2b: deferred pairs (flagged in the list), one per warp at a time with lane = sample: the rays of one pair walk the
+        // LBVH coherently.  (lane = pair left most of the CTA idle behind one or two busy lanes: a tile defers few pairs.)
+        while (nheavy) {
             int q0 = 0;
-            if (lane == 0) q0 = atomicAdd(&s_hnext, 32);
+            if (lane == 0) q0 = atomicAdd(&s_hnext, 8);
             q0 = __shfl_sync(0xffffffffu, q0, 0);
-            if (q0 >= nheavy) break;
-            int q = q0 + lane;
-            if (q < nheavy) {
-                const int idx = s_heavy[q];
+            if (q0 >= nlist) break;
+            const int e = (lane < 8 && q0 + lane < nlist) ? s_list[q0 + lane] : 0;
+            unsigned hv = __ballot_sync(0xffffffffu, e & PAIR_HEAVY);
+            while (hv) {
+                const int j = __ffs(hv) - 1;
+                hv &= hv - 1;
+                const int idx = __shfl_sync(0xffffffffu, e, j);
                 const int rl = (idx >> 6) & 63, cl = idx & 63;
                 const int ilo = (idx & PAIR_SWAP) ? TILE + cl : rl, ihi = (idx & PAIR_SWAP) ? rl : TILE + cl;
                 const TriVerts Tlo = s_tv[ilo], Thi = s_tv[ihi];
-                uint64_t mask = 0;
-                for (int i = 0; i < P.S; i++)
-                    if (ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, sm.id[ilo], sm.id[ihi], c_uv[2 * i], c_uv[2 * i + 1])) mask |= (1ull << c_perm[i]);
-                finish_pair(rl, cl, mask);
+                unsigned mask_lo = 0, mask_hi = 0;
+                for (int i0 = 0; i0 < P.S; i0 += 32) {
+                    const int i = i0 + lane, ii = min(i, P.S - 1);
+                    const bool sees = (i < P.S) && ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, sm.id[ilo], sm.id[ihi], sm.uv[2 * ii], sm.uv[2 * ii + 1]);
+                    const int bit = sm.perm[ii];
+                    mask_lo |= __reduce_or_sync(0xffffffffu, (sees && bit < 32) ? (1u << bit) : 0u);
+                    mask_hi |= __reduce_or_sync(0xffffffffu, (sees && bit >= 32) ? (1u << (bit - 32)) : 0u);
+                }
+                if (lane == 0) finish_pair(rl, cl, (uint64_t)mask_lo | ((uint64_t)mask_hi << 32));
             }
         }
         __syncthreads();
@@ -948,7 +955,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     FFParams P;
     P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.tribox = ctx->d_tribox; P.scratch = nullptr; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
     P.order = ctx->d_order;
-    P.plane = ctx->d_plane; P.pid = ctx->d_pid; P.tau = COPLANAR_TAU * ctx->ext; P.n_inner = ctx->n_nonedge;
+    P.plane = ctx->d_plane; P.pid = ctx->d_pid; P.nbr = ctx->d_nbr; P.n_inner = ctx->n_nonedge;
     { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;

@@ -54,6 +54,10 @@ void daisy_ctx_destroy(daisy_ctx *ctx);
 /* the `rands` pattern (VS/OptixPrimeFunctionality.cpp:55-63); uv = S x {u,v}, 1 <= S <= 64.  The reference
  * draws it from rand() seeded by wall-clock time, so the drop-in takes it as an input. */
 int daisy_ctx_set_samples(daisy_ctx *ctx, const float *uv, int S);
+/* diagnostic, host only (no device needed): the plane ids daisy_ctx_create assigns -- pid_out[t] >= 1 names a plane shared by
+ * triangle t and at least one other triangle (exact for axis-aligned planes, fitted in double precision within 3e-7 x scene
+ * extent otherwise), 0 = none.  The form-factor kernel skips triangles lying in the plane of a pair's own two patches. */
+int daisy_plane_ids(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int32_t *pid_out);
 /* multi-GPU (one process per GPU): this context builds and owns the row block `rank` of `nranks` equal blocks of
  * rows_per_rank = ceil(N/nranks) rounded up to a multiple of 256 when nranks > 1 (a 256-column TMA tile of the
  * residual never straddles two blocks), of 4 when nranks == 1 (default rank 0 of 1 = all rows).  Callers must not

@@ -56,3 +56,27 @@ def two_triangle_scene():
     VN = np.array([[0, 0, 1], [0, 0, -1]], np.float32)
     T = np.array([[0, 1, 2, 0, 0, 0], [3, 4, 5, 1, 1, 1]], np.int32)
     return Scene(V, VN, T, np.zeros(2, np.int32), [{"name": "w", "Kd": np.ones(3, np.float32), "Ke": np.zeros(3, np.float32), "Ks": np.zeros(3, np.float32)}], "two")
+
+
+# ---- gather tolerance (north_star: 1e-5 relative) ------------------------------------------------------------------
+REL_TOL = 1e-5
+REL_FLOOR = 1e-6  # fraction of the array's largest magnitude below which the error is judged absolutely
+
+
+def rel_err(got, want, floor_frac=REL_FLOOR):
+    """(max TRUE relative error over entries with |want| > floor, max absolute error at or below it, floor);
+    floor = floor_frac x the largest magnitude of `want`."""
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    floor = floor_frac * float(np.abs(want).max()) if want.size else 0.0
+    big = np.abs(want) > floor
+    rel = float((np.abs(got - want)[big] / np.abs(want)[big]).max()) if big.any() else 0.0
+    small = float(np.abs(got - want)[~big].max()) if (~big).any() else 0.0
+    return rel, small, floor
+
+
+def assert_rel(got, want, what, tol=REL_TOL):
+    rel, small, floor = rel_err(got, want)
+    assert rel <= tol, (what, "max relative error", rel, "floor", floor)
+    assert small <= tol * floor, (what, "absolute error below the floor", small, "floor", floor)
+    return rel
