@@ -362,7 +362,7 @@ def incumbent_block(dz, uv):
         return {"unavailable": "oracle/_ref/libdaisy_ref_cuda.so not built (needs /root/reference at build time)"}
     out = {"kernel": "parallellism::calculateRow (reference, recompiled for sm_100a)", "ours": "k_unoccluded via daisy_unoccluded_rows", "cases": []}
     cases = [("cornellbox_blacklight", scenes.load_scene_npz(os.path.join(ROOT, "tests", "golden", "cornellbox_blacklight.npz"))),
-             ("cornell_16k", scenes.cornell_box(16384))]
+             ("cornell_15k", scenes.cornell_box(15360))]  # the reference's launch geometry divides by zero from N = 16 001 patches on
     for nm, sc in cases:
         N = sc.numtriangles
         p = dz.OptixPrimeFunctionality(dz.MeshS.from_scene(sc), rands=uv)
@@ -370,14 +370,19 @@ def incumbent_block(dz, uv):
         t0 = time.time()
         ours = p.runCalculateRadiosityMatrix(0, N, 0)["m_value"]
         t_ours = time.time() - t0
-        pyref.cuda_run_calculate_radiosity_matrix(sc.vertices, sc.normals, sc.tri[:64])  # warm-up on a 64-patch slice
+        if not out["cases"]:  # warm-up (module load, managed-memory set-up); the reference's launch geometry needs a few thousand patches
+            pyref.cuda_run_calculate_radiosity_matrix(sc.vertices, sc.normals, sc.tri)
         ref, t_ref = pyref.cuda_run_calculate_radiosity_matrix(sc.vertices, sc.normals, sc.tri)
         nz = ours > 0
         same_support = bool(((ref > 0) == nz).all())
-        rel = float((np.abs(ours - ref)[nz] / ours[nz]).max()) if nz.any() else 0.0
+        # the reference binary is nvcc's default build (FMA contraction, libdevice powf): entries that are cancellation residue
+        # (1e-9 and below, against typical 1e-5 .. 1e-2) carry that rounding noise in full, hence the floor
+        big = ours > 1e-6 * float(ours.max())
+        rel = float((np.abs(ours - ref)[big] / ours[big]).max()) if big.any() else 0.0
         out["cases"].append({"scene": nm, "patches": int(N), "reference_seconds": t_ref, "ours_seconds": t_ours, "speedup": t_ref / t_ours,
                              "pairs_per_s_reference": N * N / t_ref, "pairs_per_s_ours": N * N / t_ours,
-                             "same_facing_pairs": same_support, "max_rel_diff": rel})
+                             "same_facing_pairs": same_support, "max_abs_diff": float(np.abs(ours - ref).max()),
+                             "max_rel_diff_above_1e-6_of_max": rel})
         p.close()
         del ours, ref
     return out
@@ -563,14 +568,20 @@ def run_ours(args):
         e2e_s = (time.time() - t0) / nst
         e2e = {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(2 * K * N * 4), "d2h_bytes_per_step": int(2 * K * N * 4)}
     else:
-        # multi-GPU: every rank uploads the whole residual vector and its slice of B from pinned host memory, runs one pass
-        # through the public API (exchange included) and reads back its slices plus the band sums
+        # multi-GPU: every rank uploads ONLY its own rows of B and of the residual from pinned host memory (the residual slices
+        # reach the other ranks over NVLink like the output of a pass), runs one pass through the public API (exchange
+        # included) and reads back its slices plus the band sums
         hBl = torch.empty((K, nloc), dtype=torch.float32, pin_memory=True).numpy()
         hRl = torch.empty((K, nloc), dtype=torch.float32, pin_memory=True).numpy()
+        hRin = torch.empty((K, nloc), dtype=torch.float32, pin_memory=True).numpy()
         hR = torch.empty((K, N), dtype=torch.float32, pin_memory=True).numpy()
-        hBl[:] = E[:, r0:r1]; hR[:] = E
+        hBl[:] = E[:, r0:r1]; hRin[:] = E[:, r0:r1]; hR[:] = E
+        sliced = not args.no_fused
         def e2e_step():
-            _lib.check(L.daisy_solver_write_partitioned(solver._s, _lib.fptr(hBl), _lib.fptr(hR)))
+            if sliced:
+                _lib.check(L.daisy_solver_write_slices(solver._s, _lib.fptr(hBl), _lib.fptr(hRin)))
+            else:
+                _lib.check(L.daisy_solver_write_partitioned(solver._s, _lib.fptr(hBl), _lib.fptr(hR)))
             solver.step(True)
             _lib.check(L.daisy_solver_read(solver._s, _lib.fptr(hBl), _lib.fptr(hRl)))
         for _ in range(2):
@@ -583,7 +594,8 @@ def run_ours(args):
             e2e_step()
         torch.cuda.synchronize()
         e2e_s = allmax((time.time() - t0) / nst)
-        e2e = {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(world * (K * N + K * nloc) * 4),
+        h2d = (2 * K * N * 4) if sliced else int(world * (K * N + K * nloc) * 4)
+        e2e = {"value": 1.0 / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(world * (2 * K * nloc * 4 + 8 * K * world))}
 
     # ---- whole solve with the reference's stop rule (SpectralLightning::converge_lightning, Lightning.h:145-151:
@@ -610,6 +622,27 @@ def run_ours(args):
         except Exception as ex:
             incumbent = {"unavailable": repr(ex)}
 
+    # ---- closest hit (optixQuery) through host buffers: the camera rays of an 800 x 600 window, 4 samples per pixel
+    closest = None
+    if world == 1 and rank == 0:
+        try:
+            from daisyriot_b200 import api as dzapi
+            cam = dzapi.Camera(800, 600, 4)
+            lo, hi = sc.vertices.min(0), sc.vertices.max(0)
+            mid = (np.float32(0.5) * (lo + hi)).astype(np.float32)
+            cam.dir = mid.copy()
+            cam.eye = np.array([mid[0], mid[1], hi[2] + np.float32(1.6) * (hi[2] - lo[2])], np.float32)
+            rays = np.ascontiguousarray(cam.gen_rays_for_screen(True), np.float32)
+            nr = rays.reshape(-1, 6).shape[0]
+            hits = optixP.optixQuery(nr, rays)
+            ts = []
+            for _ in range(3):
+                t0 = time.time(); optixP.optixQuery(nr, rays, hits); ts.append(time.time() - t0)
+            closest = {"metric": "closest_hit_rays_per_s through host buffers (daisy_query_closest: H2D 24 B/ray, D2H 16 B/ray)", "rays": int(nr),
+                       "value": nr / min(ts), "seconds": min(ts), "hit_fraction": float((hits["t"] > 0).mean())}
+        except Exception as ex:
+            closest = {"failed": repr(ex)}
+
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         try:
@@ -627,9 +660,9 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "reference example scene (tests/golden fixture)" if name in FIXTURE_SCENES else "synthetic",
             "config": bench_config(name, N, K, uv.shape[0], world),
-            "e2e": e2e, "gpu_launches": int((2 + (1 if K > 9 else 0) + (1 if world > 1 and not args.no_fused else 0)) * args.steps),
+            "e2e": e2e, "gpu_launches": int(L.daisy_solver_launches_per_pass(solver._s) * args.steps),
             "clocks": clocks,
-            "roofline": {"kernel": ("k_gather_mma" if K > 9 else "k_gather_tma") + "+k_gather_epilogue", "bound": "hbm", "achieved": achieved,
+            "roofline": {"kernel": ("k_split_residual+k_gather_mma+k_gather_epilogue" if K > 9 else "k_gather_tma (epilogue fused)"), "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_note": "hbm_gbs is a copy (read+write) bandwidth; this kernel only reads, so frac can exceed 1", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes},
@@ -640,7 +673,7 @@ def run_ours(args):
                            "e2e_rays_per_s": rays / ff_wall,
                            "roofline": ff_roof, "clocks": ff_clocks,
                            "ncu": ff_ncu},  # pipe / cache utilisation of the traversal kernel from the committed ncu capture of this workload
-            "parity": parity, "incumbent": incumbent,
+            "parity": parity, "incumbent": incumbent, "closest_hit": closest,
             "converge": {"rule": "sum of residual over bands and patches <= 200 (Lightning.h:145-151)", "passes": int(conv_passes),
                          "seconds": conv_s, "total_with_formfactors_s": conv_s + ff_wall},
         }

@@ -69,6 +69,27 @@ SYMBOLS = {
     "daisy_solver_write": (_i, [_vp, _fp, _fp]),
     "daisy_solver_step_local": (_i, [_vp]),
     "daisy_solver_write_partitioned": (_i, [_vp, _fp, _fp]),
+    "daisy_solver_write_slices": (_i, [_vp, _fp, _fp]),
+    "daisy_solver_launches_per_pass": (_i, [_vp]),
+    "daisy_group_create": (_i, [_fp, _i, _fp, _i, _ip, _i, _ip, _i, C.POINTER(_vp)]),
+    "daisy_group_destroy": (None, [_vp]),
+    "daisy_group_size": (_i, [_vp]),
+    "daisy_group_ctx": (_vp, [_vp, _i]),
+    "daisy_group_set_samples": (_i, [_vp, _fp, _i]),
+    "daisy_group_formfactors_build": (_i, [_vp, _i]),
+    "daisy_group_formfactors_read_rows": (_i, [_vp, _i, _i, _fp]),
+    "daisy_group_formfactors_write_rows": (_i, [_vp, _i, _i, _fp]),
+    "daisy_group_formfactors_to_csc": (_i, [_vp, _i64p, _fp, _ip, _ip]),
+    "daisy_group_formfactors_stats": (_i, [_vp, _i64p, _i64p, _dp, _dp]),
+    "daisy_group_solver_create": (_i, [_vp, _i, _fp, _fp, _i, _ip, C.POINTER(_vp)]),
+    "daisy_group_solver_destroy": (None, [_vp]),
+    "daisy_group_solver_reset": (_i, [_vp]),
+    "daisy_group_solver_step": (_i, [_vp, _dp]),
+    "daisy_group_solver_converge": (_i, [_vp, C.c_double, _i, _i, _ip]),
+    "daisy_group_solver_numpasses": (_i, [_vp]),
+    "daisy_group_solver_band_sums": (_i, [_vp, _dp]),
+    "daisy_group_solver_read": (_i, [_vp, _fp, _fp]),
+    "daisy_group_solver_write": (_i, [_vp, _fp, _fp]),
     "daisy_solver_ipc_handles": (_i, [_vp, C.c_char_p]),
     "daisy_solver_set_peers": (_i, [_vp, C.c_char_p, _i]),
     "daisy_solver_step_fused": (_i, [_vp, _dp]),

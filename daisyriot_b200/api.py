@@ -284,6 +284,123 @@ class OptixPrimeFunctionality:
                 "pairs_fallback": int(_lib.lib().daisy_formfactors_pairs_fallback(self._ctx))}
 
 
+
+class DeviceGroup:
+    """All GPUs of the box behind ONE host process (``daisy_group_*``): the reference's ``OptixPrimeFunctionality`` surface
+    for the matrix build over several devices -- row block g on ``devices[g]``, mesh and LBVH replicated, mirrored tiles
+    stored into the owners' matrices over NVLink.  ``device(i)`` gives device i's context as an ``OptixPrimeFunctionality``
+    view (row range, masks, digests, closest hit)."""
+
+    def __init__(self, mesh: MeshS, devices=None, ndev: int | None = None, rands=None, seed: int = 1):
+        L = _lib.lib()
+        self.mesh, self.N = mesh, mesh.numtriangles
+        if devices is None:
+            devices = list(range(ndev if ndev is not None else L.daisy_device_count()))
+        self.devices = [int(d) for d in devices]
+        dev = np.ascontiguousarray(self.devices, np.int32)
+        v = np.ascontiguousarray(mesh.vertices, np.float32)
+        n = np.ascontiguousarray(mesh.normals, np.float32)
+        t = np.ascontiguousarray(mesh.triangleIndices, np.int32)
+        self._g = C.c_void_p()
+        _lib.check(L.daisy_group_create(_lib.fptr(v), v.shape[0], _lib.fptr(n), n.shape[0], _lib.iptr(t), t.shape[0], _lib.iptr(dev), len(self.devices),
+                                        C.byref(self._g)), "group_create")
+        self.rands = np.ascontiguousarray(msvc_sample_pattern(seed, RAYS_PER_PATCH) if rands is None else rands, np.float32)
+        _lib.check(L.daisy_group_set_samples(self._g, _lib.fptr(self.rands), self.rands.shape[0]), "group_set_samples")
+
+    def close(self):
+        if getattr(self, "_g", None):
+            _lib.lib().daisy_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device(self, i: int) -> "OptixPrimeFunctionality":
+        view = OptixPrimeFunctionality.__new__(OptixPrimeFunctionality)
+        view.mesh, view.N, view.rands = self.mesh, self.N, self.rands
+        view._ctx = C.c_void_p(_lib.lib().daisy_group_ctx(self._g, i))
+        view.rank, view.nranks = i, len(self.devices)
+        view.close = lambda: None  # the group owns the context
+        return view
+
+    def cudaCalculateRadiosityMatrix(self):
+        _lib.check(_lib.lib().daisy_group_formfactors_build(self._g, _lib.FF_DEVICE), "group_formfactors_build")
+        return self
+
+    def calculateRadiosityMatrix(self):
+        _lib.check(_lib.lib().daisy_group_formfactors_build(self._g, _lib.FF_HOST), "group_formfactors_build")
+        return self
+
+    def rows(self, row0=0, nrows=None) -> np.ndarray:
+        nrows = self.N - row0 if nrows is None else nrows
+        out = np.empty((nrows, self.N), np.float32)
+        _lib.check(_lib.lib().daisy_group_formfactors_read_rows(self._g, row0, nrows, _lib.fptr(out)), "group_formfactors_read_rows")
+        return out
+
+    def stats(self):
+        p, r, a, b = C.c_int64(), C.c_int64(), C.c_double(), C.c_double()
+        _lib.check(_lib.lib().daisy_group_formfactors_stats(self._g, C.byref(p), C.byref(r), C.byref(a), C.byref(b)))
+        return {"pairs": p.value, "rays": r.value, "lbvh_ms": a.value, "ff_ms": b.value}
+
+
+class GroupSolver:
+    """The Lightning family's solver over a :class:`DeviceGroup` (``daisy_group_solver_*``): same calls as the single-GPU
+    solver, whole-scene ``K x N`` arrays in and out; a pass is one asynchronous kernel launch per device."""
+
+    def __init__(self, group: DeviceGroup, K: int, E, M, mat_idx):
+        self.group, self.K = group, K
+        E = np.ascontiguousarray(E, np.float32)
+        M = np.ascontiguousarray(M, np.float32)
+        mat = np.ascontiguousarray(mat_idx, np.int32)
+        self._s = C.c_void_p()
+        _lib.check(_lib.lib().daisy_group_solver_create(group._g, K, _lib.fptr(E), _lib.fptr(M), M.shape[0], _lib.iptr(mat), C.byref(self._s)),
+                   "group_solver_create")
+
+    def close(self):
+        if getattr(self, "_s", None):
+            _lib.lib().daisy_group_solver_destroy(self._s)
+            self._s = None
+
+    def reset(self):
+        _lib.check(_lib.lib().daisy_group_solver_reset(self._s), "group_solver_reset")
+
+    def step(self, want_sums: bool = True):
+        if not want_sums:
+            _lib.check(_lib.lib().daisy_group_solver_step(self._s, None), "group_solver_step")
+            return None
+        sums = np.zeros(self.K, np.float64)
+        _lib.check(_lib.lib().daisy_group_solver_step(self._s, sums.ctypes.data_as(C.POINTER(C.c_double))), "group_solver_step")
+        return sums
+
+    def band_sums(self):
+        sums = np.zeros(self.K, np.float64)
+        _lib.check(_lib.lib().daisy_group_solver_band_sums(self._s, sums.ctypes.data_as(C.POINTER(C.c_double))), "group_solver_band_sums")
+        return sums
+
+    def converge(self, threshold: float, per_band: bool, max_passes: int = 0) -> int:
+        passes = C.c_int()
+        _lib.check(_lib.lib().daisy_group_solver_converge(self._s, float(threshold), int(per_band), max_passes, C.byref(passes)), "group_solver_converge")
+        return passes.value
+
+    @property
+    def numpasses(self):
+        return int(_lib.lib().daisy_group_solver_numpasses(self._s))
+
+    def read(self):
+        B = np.empty((self.K, self.group.N), np.float32)
+        R = np.empty((self.K, self.group.N), np.float32)
+        _lib.check(_lib.lib().daisy_group_solver_read(self._s, _lib.fptr(B), _lib.fptr(R)), "group_solver_read")
+        return B, R
+
+    def write(self, B, R):
+        B = np.ascontiguousarray(B, np.float32)
+        R = np.ascontiguousarray(R, np.float32)
+        _lib.check(_lib.lib().daisy_group_solver_write(self._s, _lib.fptr(B), _lib.fptr(R)), "group_solver_write")
+
+
 def row_digest_host(F_rows: np.ndarray):
     """The digests of :meth:`RadMat.row_digest` from host rows (rows x N float32)."""
     bits = np.ascontiguousarray(F_rows, np.float32).view(np.uint32)

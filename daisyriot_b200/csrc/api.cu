@@ -27,7 +27,7 @@ extern "C" int daisy_device_count(void) {
 
 static void free_ctx(daisy_ctx *c) {
     if (!c) return;
-    if (c->peers_set)
+    if (c->peers_set && c->peers_ipc)
         for (int g = 0; g < c->nranks && g < 16; g++)
             if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
     cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane); cudaFree(c->d_pid); cudaFree(c->d_nbr);
@@ -223,6 +223,7 @@ extern "C" int daisy_ctx_create(const float *vertices, int nv, const float *norm
                                 int device, daisy_ctx **out) {
     DZ_REQUIRE(out, DAISY_E_INVALID, "daisy_ctx_create: null out pointer");
     *out = nullptr;
+    DzRange range_("daisy_ctx_create: mesh upload, plane ids, LBVH, patch records");
     DZ_REQUIRE(nv >= 0 && nn >= 0 && ntri >= 0, DAISY_E_INVALID, "daisy_ctx_create: negative count");
     DZ_REQUIRE(ntri == 0 || (vertices && normals && tri_idx), DAISY_E_INVALID, "daisy_ctx_create: null array");
     for (int i = 0; i < ntri; i++)
@@ -326,6 +327,8 @@ extern "C" int daisy_ctx_row_range(daisy_ctx *ctx, int *row0, int *row1, int *ro
 
 extern "C" int daisy_ctx_set_stream(daisy_ctx *ctx, void *cuda_stream) {
     DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_ctx_set_stream: null context");
+    DZ_CUDA(cudaSetDevice(ctx->device));
+    DZ_CUDA(cudaDeviceSynchronize()); // work enqueued on the previous stream (context set-up) is complete before the new one is used
     ctx->stream = (cudaStream_t)cuda_stream;
     return DAISY_OK;
 }
@@ -399,6 +402,7 @@ extern "C" int daisy_formfactors_build(daisy_ctx *ctx, int variant) {
     DZ_REQUIRE(ctx, DAISY_E_INVALID, "daisy_formfactors_build: null context");
     DZ_REQUIRE(variant == DAISY_FF_DEVICE || variant == DAISY_FF_HOST, DAISY_E_INVALID, "daisy_formfactors_build: bad variant");
     DZ_REQUIRE(ctx->S >= 1, DAISY_E_STATE, "daisy_formfactors_build: call daisy_ctx_set_samples first");
+    DzRange range_("daisy_formfactors_build: fused form factors + visibility (k_ff_tiles)");
     DZ_CUDA(cudaSetDevice(ctx->device));
     int rc = ensure_F(ctx);
     if (rc) return rc;
@@ -445,6 +449,17 @@ extern "C" int daisy_formfactors_set_peers(daisy_ctx *ctx, const void *handles, 
         ctx->peerF[g] = (float *)p;
     }
     ctx->peers_set = true;
+    ctx->peers_ipc = true;
+    return DAISY_OK;
+}
+
+int dz_ctx_set_peer_pointers(daisy_ctx *ctx, float *const *F, int nranks) {
+    DZ_REQUIRE(ctx && F, DAISY_E_INVALID, "set_peer_pointers: null argument");
+    DZ_REQUIRE(nranks == ctx->nranks && nranks <= 16, DAISY_E_INVALID, "set_peer_pointers: nranks must match the partition (<= 16)");
+    DZ_REQUIRE(ctx->d_F && !ctx->peers_set, DAISY_E_STATE, "set_peer_pointers: allocate first, set once");
+    for (int g = 0; g < nranks; g++) ctx->peerF[g] = F[g];
+    ctx->peers_set = true;
+    ctx->peers_ipc = false;
     return DAISY_OK;
 }
 
@@ -524,6 +539,7 @@ extern "C" int daisy_visibility_masks(daisy_ctx *ctx, int variant, int row0, int
     DZ_REQUIRE(ctx->S >= 1, DAISY_E_STATE, "daisy_visibility_masks: call daisy_ctx_set_samples first");
     DZ_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= ctx->N, DAISY_E_INVALID, "daisy_visibility_masks: rows out of range");
     if (nrows == 0 || ctx->N == 0) return DAISY_OK;
+    DzRange range_("daisy_visibility_masks");
     DZ_CUDA(cudaSetDevice(ctx->device));
     int rc = dz_set_samples_const(ctx);
     if (rc) return rc;

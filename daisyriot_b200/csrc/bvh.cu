@@ -195,6 +195,7 @@ __global__ void k_tile_order(const uint64_t *__restrict__ keys, int N, int nslot
 }
 
 int dz_build_lbvh(daisy_ctx *ctx) {
+    DzRange range_("lbvh build: morton, sort, hierarchy, refit, pack");
     int N = ctx->N;
     cudaStream_t st = ctx->stream;
     cudaEvent_t e0, e1;

@@ -34,6 +34,7 @@ __device__ __forceinline__ daisy_hit closest_hit(const BvhNode *__restrict__ nod
         if (hl && hr) {
             int nearc = nd.d.x, farc = nd.d.y;
             if (tr < tl) { nearc = nd.d.y; farc = nd.d.x; }
+            DZ_ASSERT(sp < 64);
             stack[sp++] = farc;
             cur = nearc;
         } else if (hl) cur = nd.d.x;

@@ -4,7 +4,14 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/daisy_b200.h"
+
+// NVTX range over a scope (Nsight Systems / Compute timelines; a no-op function pointer when no tool is attached)
+struct DzRange {
+    explicit DzRange(const char *name) { nvtxRangePushA(name); }
+    ~DzRange() { nvtxRangePop(); }
+};
 
 // ---------------------------------------------------------------------------------------------------------
 // error plumbing (C-ABI never throws; the C++ shim above it reproduces the reference's print-and-continue)
@@ -21,6 +28,20 @@ void daisy_set_error(const char *fmt, ...);
     do {                                                    \
         if (!(cond)) { daisy_set_error("%s", msg); return code; } \
     } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-side bounds / invariant checks, compiled in with -DDAISY_BOUNDS_CHECK (`make TAG=check EXTRA=-DDAISY_BOUNDS_CHECK`):
+// a violated check prints its location and traps, which the host sees as a launch failure.  This is the memory-safety
+// net of this repo: compute-sanitizer is closed on the GPU pool the kernels are developed on, so the checked build is run
+// over the small parity cases instead (tools/checked_build.sh), next to the bit-exact comparison with the CPU oracle.
+#ifdef DAISY_BOUNDS_CHECK
+#define DZ_ASSERT(cond)                                                                                  \
+    do {                                                                                                 \
+        if (!(cond)) { printf("DZ_ASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); __trap(); } \
+    } while (0)
+#else
+#define DZ_ASSERT(cond) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // Exactly-rounded FP32 ops that ptxas may never contract into FMAs.  The reference's host build (MSVC x64,
@@ -191,6 +212,15 @@ __device__ __forceinline__ bool ray_box_fma(f3 oi, f3 inv, float lox, float loy,
     return tn <= tf * 1.00001f + 1e-30f;
 }
 
+// the same for rays whose direction signs are known: (nx, ny, nz) = the box planes the ray enters through, (fx, fy, fz) = the
+// ones it leaves through.  For finite operands min(t0, t1) IS the entry-plane value, so the result equals ray_box_fma's; a
+// NaN is dropped by the 3-input min / max here as there, which can only make the test more permissive.
+__device__ __forceinline__ bool ray_box_sorted(f3 oi, f3 inv, float nx, float ny, float nz, float fx, float fy, float fz, float tmax) {
+    const float tn = fmaxf(fmaxf(fmaf(nx, inv.x, -oi.x), fmaf(ny, inv.y, -oi.y)), fmaxf(fmaf(nz, inv.z, -oi.z), 0.0f));
+    const float tf = fminf(fminf(fmaf(fx, inv.x, -oi.x), fmaf(fy, inv.y, -oi.y)), fminf(fmaf(fz, inv.z, -oi.z), tmax));
+    return tn <= tf * 1.00001f + 1e-30f;
+}
+
 // per-triangle vertex record (48 B): float4 a, b, c (w unused)
 struct __align__(16) TriVerts { float4 a, b, c; };
 // per-patch record for the 4x4 rule (80 B): 4 sub-centroids with sub-areas in w, then normal with area in w
@@ -233,6 +263,7 @@ struct daisy_ctx {
     bool have_F = false;
     float *peerF[16] = { nullptr }; // every rank's F (own pointer or CUDA-IPC mapping), set by daisy_formfactors_set_peers
     bool peers_set = false;
+    bool peers_ipc = false;         // the peer pointers are CUDA-IPC mappings this context has to close (one process per GPU)
     int64_t pairs_traced = 0, pairs_owned = 0, pairs_heavy = 0;
     double ff_ms = 0.0;
     int num_sms = 148;
@@ -243,4 +274,9 @@ int dz_launch_closest(daisy_ctx *ctx, int n, const float *d_rays, daisy_hit *d_h
 int dz_precompute_geom(daisy_ctx *ctx);                              // formfactor.cu
 int dz_set_samples_const(daisy_ctx *ctx);                            // formfactor.cu
 int dz_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_tripl *d_out); // formfactor.cu
+struct daisy_solver;
+// same-process peers (daisy_group): device pointers handed over directly, peer access enabled by the caller
+int dz_ctx_set_peer_pointers(daisy_ctx *ctx, float *const *F, int nranks);                                           // api.cu
+int dz_solver_get_buffers(daisy_solver *s, float **res0, float **res1, unsigned long long **flags);                  // gather.cu
+int dz_solver_set_peer_pointers(daisy_solver *s, float *const *res0, float *const *res1, unsigned long long *const *flags, int nranks); // gather.cu
 int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mrow0, int mrow1, bool write_F); // formfactor.cu

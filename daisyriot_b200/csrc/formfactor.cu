@@ -19,7 +19,7 @@
 #define NBR_CAP 32 // ints per triangle in the neighbour table: [0] = count, then up to 31 triangles of its own plane
 #define FF_THREADS 256
 #ifndef FF_MINBLOCKS
-#define FF_MINBLOCKS 3
+#define FF_MINBLOCKS 4
 #endif
 #define PI_D 3.14159265358979323846
 #define PI_F 3.14159265358979323846f
@@ -162,7 +162,7 @@ __global__ void k_tri_planes(const TriVerts *__restrict__ tv, const float4 *__re
                 const bool same_plane = my_pid != 0 && pid[k] == my_pid;
                 if (same_plane) { // goes on this patch's neighbour list: the only triangles of its plane its edge samples have to test
                     if (n_nbr == NBR_CAP - 1) safe = false;
-                    else my_nbr[1 + n_nbr++] = k;
+                    else { DZ_ASSERT(1 + n_nbr < NBR_CAP); my_nbr[1 + n_nbr++] = k; }
                 }
                 if (dist <= 4.0 * tau || same_plane) { // coplanar neighbour
                     const d3 f1 = dsub(Q[1], Q[0]), f2 = dsub(Q[2], Q[0]), f3 = dsub(Q[2], Q[1]);
@@ -180,7 +180,7 @@ __global__ void k_tri_planes(const TriVerts *__restrict__ tv, const float4 *__re
         const BvhNode nd = nodes[cur];
         const bool hl = !(nd.a.x > b1.x || nd.a.w < b0.x || nd.a.y > b1.y || nd.b.x < b0.y || nd.a.z > b1.z || nd.b.y < b0.z);
         const bool hr = !(nd.b.z > b1.x || nd.c.y < b0.x || nd.b.w > b1.y || nd.c.z < b0.y || nd.c.x > b1.z || nd.c.w < b0.z);
-        if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
+        if (hl && hr) { DZ_ASSERT(sp < 64); stack[sp++] = nd.d.y; cur = nd.d.x; }
         else if (hl) cur = nd.d.x;
         else if (hr) cur = nd.d.y;
         else {
@@ -287,8 +287,10 @@ int dz_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_t
 // occlusion query bounded by the hit on hi itself: the ray sees hi iff the watertight test accepts hi at t_hi and
 // no other triangle k is accepted with (t_k, k) < (t_hi, hi) lexicographically -- the same predicate, but the
 // traversal can stop at the first occluder and never looks beyond t_hi.
+// skip_lo / skip_hi: plane ids whose triangles this ray cannot touch (coplanar skipping, see the kernel; 0 = none): children
+// of a node lying entirely in such a plane are not entered.
 __device__ __noinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root,
-                                         const TriVerts &Tlo, const TriVerts &Thi, int lo, int hi, float u, float v) {
+                                         const TriVerts &Tlo, const TriVerts &Thi, int lo, int hi, float u, float v, int skip_lo, int skip_hi) {
     // uv2xyz: a + u*(b-a) + v*(c-a)                                                   triangle_math.cpp:3-9
     f3 a0 = xyz(Tlo.a), a1 = xyz(Thi.a);
     f3 org = e_add(e_add(a0, e_scale(e_sub(xyz(Tlo.b), a0), u)), e_scale(e_sub(xyz(Tlo.c), a0), v));
@@ -318,9 +320,11 @@ __device__ __noinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const T
         }
         BvhNode nd = nodes[cur];
         float tl, tr;
-        bool hl = ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, thi, tl);
-        bool hr = ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, thi, tr);
-        if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
+        const bool sl = nd.d.z != 0 && (nd.d.z == skip_lo || nd.d.z == skip_hi);
+        const bool sr = nd.d.w != 0 && (nd.d.w == skip_lo || nd.d.w == skip_hi);
+        bool hl = !sl && ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, thi, tl);
+        bool hr = !sr && ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, thi, tr);
+        if (hl && hr) { DZ_ASSERT(sp < 64); stack[sp++] = nd.d.y; cur = nd.d.x; }
         else if (hl) cur = nd.d.x;
         else if (hr) cur = nd.d.y;
         else {
@@ -414,15 +418,15 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
         bool hr = !sr && shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
         if (hl && nd.d.x < 0) {
             const int k = ~nd.d.x;
-            if (k != lo && k != hi) { if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
+            if (k != lo && k != hi) { DZ_ASSERT(k >= 0 && n_main <= SHAFT_CAP); if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
             hl = false;
         }
         if (hr && nd.d.y < 0) {
             const int k = ~nd.d.y;
-            if (k != lo && k != hi) { if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
+            if (k != lo && k != hi) { DZ_ASSERT(k >= 0 && n_main <= SHAFT_CAP); if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
             hr = false;
         }
-        if (hl && hr) { stack[sp++] = nd.d.y; cur = nd.d.x; }
+        if (hl && hr) { DZ_ASSERT(sp < 64); stack[sp++] = nd.d.y; cur = nd.d.x; }
         else if (hl) cur = nd.d.x;
         else if (hr) cur = nd.d.y;
         else {
@@ -431,6 +435,30 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
         }
     }
     return overflow ? -1 : n_main;
+}
+
+// Premise of coplanar skipping per side of a pair: the patch qualifies (plane.w = its smallest altitude h > 0, k_tri_planes)
+// and every ray meets its plane steeply.  The ray directions are convex combinations of the three vertex-to-vertex vectors
+// D_i, so n.D_i of one sign bounds cos(theta) >= min|n.D_i| / max|D_i|.  The edge functions of a coplanar triangle near a
+// patch are computed from coordinates relative to the ray origin: rounding ~ 8 eps (distance) (its size), against a true
+// value >= (margin h)(its edge) cos(theta).  With sizes and aspect ratios bounded by k_tri_planes that gives cos >= 0.02 on
+// the origin side (distance ~ size) and margin h cos >= 128 eps (distance) on the destination side.  on_lo / on_hi: the side's
+// plane may be skipped by every sample whose barycentric margin is at least m_req (<= EDGE_MARGIN, so by all inner samples).
+__device__ __forceinline__ void pair_premise(const TriVerts &A, const TriVerts &B, float4 pl, float4 ph, bool &on_lo, bool &on_hi, float &m_req) {
+    const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
+    const float d1x = B.b.x - A.b.x, d1y = B.b.y - A.b.y, d1z = B.b.z - A.b.z;
+    const float d2x = B.c.x - A.c.x, d2y = B.c.y - A.c.y, d2z = B.c.z - A.c.z;
+    const float dmax = sqrtf(fmaxf(d0x * d0x + d0y * d0y + d0z * d0z, fmaxf(d1x * d1x + d1y * d1y + d1z * d1z, d2x * d2x + d2y * d2y + d2z * d2z)));
+    const float l0 = pl.x * d0x + pl.y * d0y + pl.z * d0z, l1 = pl.x * d1x + pl.y * d1y + pl.z * d1z, l2 = pl.x * d2x + pl.y * d2y + pl.z * d2z;
+    const float h0 = ph.x * d0x + ph.y * d0y + ph.z * d0z, h1 = ph.x * d1x + ph.y * d1y + ph.z * d1z, h2 = ph.x * d2x + ph.y * d2y + ph.z * d2z;
+    const float lmin = ((l0 > 0.f) == (l1 > 0.f) && (l1 > 0.f) == (l2 > 0.f)) ? fminf(fabsf(l0), fminf(fabsf(l1), fabsf(l2))) : 0.f;
+    const float hmin = ((h0 > 0.f) == (h1 > 0.f) && (h1 > 0.f) == (h2 > 0.f)) ? fminf(fabsf(h0), fminf(fabsf(h1), fabsf(h2))) : 0.f;
+    // required margins (fractions of the altitude): m >= 128 eps D / (h cos), D = 32 h on the origin side
+    const float mlo = (pl.w > 0.f && lmin > 0.f) ? 2.44e-4f * dmax / lmin : 1.f;
+    const float mhi = (ph.w > 0.f && hmin > 0.f) ? 7.63e-6f * (dmax + 64.f * ph.w) * dmax / (hmin * ph.w) : 1.f;
+    on_lo = mlo <= EDGE_MARGIN;
+    on_hi = mhi <= EDGE_MARGIN;
+    m_req = fmaxf(on_lo ? mlo : 0.f, on_hi ? mhi : 0.f);
 }
 
 // Visibility mask of one pair with the whole warp: lane = sample (device order), a candidate list is walked in lock step
@@ -464,6 +492,12 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         // Slab tests run in lock step over the list (uniform box loads); a lane that passes one only QUEUES the
         // triangle.  The expensive watertight tests are then issued for whole queues at a time, so a warp instruction
         // slot is spent on them only when many lanes have one pending, not whenever a single lane does.
+        // do all rays of this pass enter every box through the same three planes?  (same signs of the direction components)
+        const unsigned act = __ballot_sync(0xffffffffu, i < S);
+        const unsigned bx = __ballot_sync(0xffffffffu, i < S && inv.x < 0.f), by = __ballot_sync(0xffffffffu, i < S && inv.y < 0.f),
+                       bz = __ballot_sync(0xffffffffu, i < S && inv.z < 0.f);
+        const bool neg_x = bx != 0, neg_y = by != 0, neg_z = bz != 0;
+        const bool sorted = (bx == 0 || bx == act) && (by == 0 || by == act) && (bz == 0 || bz == act);
         int qlen = 0;
         unsigned qreg = 0; // queued candidates: 4-bit positions inside the staged chunk of 16
         auto flush = [&]() {
@@ -480,6 +514,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
 #endif
                 if (alive && t < qlen) {
                     const int k = wk[(qreg >> (4 * t)) & 15];
+                    DZ_ASSERT(k >= 0 && qlen <= FF_QCAP);
                     TriVerts tr = tv[k];
                     if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) alive = false;
                 }
@@ -499,9 +534,12 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 __syncwarp();
                 if (lane < nb) {
                     const int k = __ldcg(cand + c0 + lane);
+                    DZ_ASSERT(k >= 0 && c0 + lane < SHAFT_CAP);
                     wk[lane] = k;
-                    wb[2 * lane] = tribox[2 * (size_t)k];
-                    wb[2 * lane + 1] = tribox[2 * (size_t)k + 1];
+                    const float4 lo4 = tribox[2 * (size_t)k], hi4 = tribox[2 * (size_t)k + 1];
+                    // rays of one sign pattern (nearly always: they are almost parallel): entry planes first, exit planes second
+                    wb[2 * lane] = sorted ? make_float4(neg_x ? hi4.x : lo4.x, neg_y ? hi4.y : lo4.y, neg_z ? hi4.z : lo4.z, 0.f) : lo4;
+                    wb[2 * lane + 1] = sorted ? make_float4(neg_x ? lo4.x : hi4.x, neg_y ? lo4.y : hi4.y, neg_z ? lo4.z : hi4.z, 0.f) : hi4;
                 }
                 __syncwarp();
                 for (int j0 = 0; j0 < nb; j0 += FF_QCAP) {
@@ -510,7 +548,9 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                         const int j = j0 + jj;
                         if (j < nb) {
                             const float4 b0 = wb[2 * j], b1 = wb[2 * j + 1];
-                            if (alive && ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)) { qreg |= (unsigned)j << (4 * qlen); qlen++; }
+                            const bool near_enough = sorted ? ray_box_sorted(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi)
+                                                           : ray_box_fma(oi, inv, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thi);
+                            if (alive && near_enough) { qreg |= (unsigned)j << (4 * qlen); qlen++; }
                         }
                     }
 #ifdef DAISY_FF_STATS
@@ -673,6 +713,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
         // masked out by id < 0
         if (tid < 2 * TILE) {
             const int t = P.order[(tid < TILE ? R0 : C0 - TILE) + tid];
+            DZ_ASSERT(t >= -1 && t < P.N);
             const int tt = max(t, 0);
             sm.id[tid] = t;
             sm.pl[tid] = P.plane[tt];
@@ -716,7 +757,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 int leader = __ffs(m) - 1;
                 if (lane == leader) base = atomicAdd(&s_nlist, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (trace) s_list[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)(idx | (r > c ? PAIR_SWAP : 0));
+                if (trace) { DZ_ASSERT(base + __popc(m & ((1u << lane) - 1)) < TILE * TILE); s_list[base + __popc(m & ((1u << lane) - 1))] = (unsigned short)(idx | (r > c ? PAIR_SWAP : 0)); }
             }
         }
         __syncthreads();
@@ -786,23 +827,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 // aspect ratios bounded by k_tri_planes that gives cos >= 0.02 on the origin side (distance ~ size) and
                 // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
                 bool on_lo = false, on_hi = false;
-                if (P.ring_on) {
-                    const float4 pl = sm.pl[ilo], ph = sm.pl[ihi];
-                    const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
-                    const float d1x = B.b.x - A.b.x, d1y = B.b.y - A.b.y, d1z = B.b.z - A.b.z;
-                    const float d2x = B.c.x - A.c.x, d2y = B.c.y - A.c.y, d2z = B.c.z - A.c.z;
-                    const float dmax = sqrtf(fmaxf(d0x * d0x + d0y * d0y + d0z * d0z, fmaxf(d1x * d1x + d1y * d1y + d1z * d1z, d2x * d2x + d2y * d2y + d2z * d2z)));
-                    const float l0 = pl.x * d0x + pl.y * d0y + pl.z * d0z, l1 = pl.x * d1x + pl.y * d1y + pl.z * d1z, l2 = pl.x * d2x + pl.y * d2y + pl.z * d2z;
-                    const float h0 = ph.x * d0x + ph.y * d0y + ph.z * d0z, h1 = ph.x * d1x + ph.y * d1y + ph.z * d1z, h2 = ph.x * d2x + ph.y * d2y + ph.z * d2z;
-                    const float lmin = ((l0 > 0.f) == (l1 > 0.f) && (l1 > 0.f) == (l2 > 0.f)) ? fminf(fabsf(l0), fminf(fabsf(l1), fabsf(l2))) : 0.f;
-                    const float hmin = ((h0 > 0.f) == (h1 > 0.f) && (h1 > 0.f) == (h2 > 0.f)) ? fminf(fabsf(h0), fminf(fabsf(h1), fabsf(h2))) : 0.f;
-                    // required margins (fractions of the altitude): m >= 128 eps D / (h cos), D = 32 h on the origin side
-                    const float mlo = (pl.w > 0.f && lmin > 0.f) ? 2.44e-4f * dmax / lmin : 1.f;
-                    const float mhi = (ph.w > 0.f && hmin > 0.f) ? 7.63e-6f * (dmax + 64.f * ph.w) * dmax / (hmin * ph.w) : 1.f;
-                    on_lo = mlo <= EDGE_MARGIN; // inner samples (margin >= EDGE_MARGIN) are then always safe
-                    on_hi = mhi <= EDGE_MARGIN;
-                    m_req = fmaxf(on_lo ? mlo : 0.f, on_hi ? mhi : 0.f);
-                }
+                if (P.ring_on) pair_premise(A, B, sm.pl[ilo], sm.pl[ihi], on_lo, on_hi, m_req);
                 ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand);
                 if (ncand >= 0) ncand |= (on_lo ? 0x10000 : 0) | (on_hi ? 0x20000 : 0);
                 if (ncand < 0) { // the lists do not fit: flag the pair, phase 2b walks the LBVH per ray
@@ -863,10 +888,17 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 const int rl = (idx >> 6) & 63, cl = idx & 63;
                 const int ilo = (idx & PAIR_SWAP) ? TILE + cl : rl, ihi = (idx & PAIR_SWAP) ? rl : TILE + cl;
                 const TriVerts Tlo = s_tv[ilo], Thi = s_tv[ihi];
+                bool on_lo = false, on_hi = false;
+                float m_req = 0.f;
+                if (P.ring_on) pair_premise(Tlo, Thi, sm.pl[ilo], sm.pl[ihi], on_lo, on_hi, m_req);
                 unsigned mask_lo = 0, mask_hi = 0;
                 for (int i0 = 0; i0 < P.S; i0 += 32) {
                     const int i = i0 + lane, ii = min(i, P.S - 1);
-                    const bool sees = (i < P.S) && ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, sm.id[ilo], sm.id[ihi], sm.uv[2 * ii], sm.uv[2 * ii + 1]);
+                    const float su = sm.uv[2 * ii], sv = sm.uv[2 * ii + 1];
+                    // the pair's own planes are skipped by the samples far enough from the patch edges; the others walk everything
+                    const bool inner = fminf(fminf(su, sv), 1.0f - su - sv) >= m_req;
+                    const bool sees = (i < P.S) && ray_sees(P.nodes, P.tv, P.root, Tlo, Thi, sm.id[ilo], sm.id[ihi], su, sv,
+                                                            (inner && on_lo) ? sm.pid[ilo] : 0, (inner && on_hi) ? sm.pid[ihi] : 0);
                     const int bit = sm.perm[ii];
                     mask_lo |= __reduce_or_sync(0xffffffffu, (sees && bit < 32) ? (1u << bit) : 0u);
                     mask_hi |= __reduce_or_sync(0xffffffffu, (sees && bit >= 32) ? (1u << (bit - 32)) : 0u);
@@ -888,8 +920,9 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                         const float v = diag ? ((a < b) ? s_rc[a][b] : ((a > b) ? s_cr[a][b] : 0.0f)) : s_rc[a][b];
                         if (P.peer_mode) {
                             const int g = r / P.n_per_rank;
+                            DZ_ASSERT(g >= 0 && g < 16 && P.Fpeer[g] != nullptr && c < P.N);
                             P.Fpeer[g][(size_t)(r - g * P.n_per_rank) * P.ldF + c] = v;
-                        } else if (r >= P.row0 && r < P.row1) P.F[(size_t)(r - P.row0) * P.ldF + c] = v;
+                        } else if (r >= P.row0 && r < P.row1) { DZ_ASSERT(c < P.N && (int64_t)c < P.ldF); P.F[(size_t)(r - P.row0) * P.ldF + c] = v; }
                     }
                 }
                 if (!diag) { // mirrored tile: row = column patch

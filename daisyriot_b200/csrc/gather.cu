@@ -42,9 +42,15 @@ struct daisy_solver {
     float *d_partial = nullptr; // nsplit x nloc x Kp
     double *d_cta_sums = nullptr;
     unsigned int *d_done = nullptr;
+    unsigned int *d_rb_arrive = nullptr; // fused epilogue (k_gather_tma): column splits finished per row block
+    double *d_rb_sums = nullptr;         // per row block band sums
+    int nrb_tma = 0;
+    unsigned long long *h_abort = nullptr, *d_abort_host = nullptr; // host-mapped abort marker of the fused exchange
+    unsigned long long timeout_ns = 30000000000ull;                  // how long a pass waits for a peer's block (DAISY_EXCHANGE_TIMEOUT_MS)
     int R = 8, nsplit = 1, grid = 148, colw = 0;
     bool use_tma = true;
     bool use_mma = false;               // K = 16 / 32: tcgen05 3xTF32 path (gather_mma.cuh)
+    bool fused_epi = false;             // k_gather_tma does the epilogue (and the exchange wait) itself: one launch per pass
     float *d_split = nullptr;           // [Rh; Rl]: 2*Kp x ncolsP, rewritten at the start of every pass
     int ncolsP = 0;
     alignas(64) CUtensorMap tmF;        // F rows of this rank: 2-D (ldF x nloc), box 128 x tile rows
@@ -54,6 +60,7 @@ struct daisy_solver {
     // fused exchange (multi-GPU): the epilogue stores this rank's block straight into every rank's next buffer through
     // CUDA-IPC mappings (NVLink), then raises flag[rank] = pass sequence number in every rank's flag array
     bool fused = false;
+    bool peers_ipc = false;                            // peer pointers are CUDA-IPC mappings to be closed (one process per GPU)
     float *peer_res[2][16] = { { nullptr } };          // [buffer][rank] base of that rank's exchange buffer
     unsigned long long *peer_flags[16] = { nullptr };  // [rank] base of that rank's flag array
     unsigned long long *d_flags = nullptr;             // own flag array (16 entries) + [16] = wait timeout marker
@@ -250,12 +257,49 @@ template <int K>
 __host__ __device__ constexpr int tma_rows() { return TmaCfg<K>::RW * TmaCfg<K>::NCW; }
 template <int K>
 __host__ __device__ constexpr int tma_stage_bytes() { return (tma_rows<K>() + K) * TmaCfg<K>::COLS * 4; }
+// shared memory kept back for the fused epilogue: the block's K sums per row (single column split: they never leave the SM)
+// and the scratch of the ordered band-sum reductions
 template <int K>
-__host__ __device__ constexpr int tma_nstage() { return (227 * 1024 - 256) / tma_stage_bytes<K>() > 8 ? 8 : (227 * 1024 - 256) / tma_stage_bytes<K>(); }
+__host__ __device__ constexpr int tma_epi_bytes() { return 2 * tma_rows<K>() * K * 4 + 2048 + 64; }
+template <int K>
+__host__ __device__ constexpr int tma_nstage() {
+    return (227 * 1024 - 256 - tma_epi_bytes<K>()) / tma_stage_bytes<K>() > 8 ? 8 : (227 * 1024 - 256 - tma_epi_bytes<K>()) / tma_stage_bytes<K>();
+}
+
+// What used to be a second kernel (k_gather_epilogue) and, multi-GPU, a third one in front (k_wait_flags), folded into the
+// streaming kernel:
+//  * the CTA that completes the LAST column split of a row block (per-block arrival counter) sums the splits in split order,
+//    applies the material matrices, accumulates B, stores the block's new residual -- into this rank's exchange block or,
+//    fused exchange, into every rank's buffer over NVLink -- and leaves the block's band sums in rb_sums;
+//  * the CTA that completes the last row block of the pass totals the band sums in block order and publishes them (and,
+//    fused exchange, raises flag[rank] = seq in every rank's flag array);
+//  * fused exchange: the producer lane polls flag[g] >= wait_seq only right before the first residual tile of rank g's block,
+//    so the stream starts on the blocks that have already arrived (the F tile of that step is already in flight).
+// A peer that does not show up within timeout_ns sets the abort markers (device flag word 16 and a host-mapped word): this
+// pass then publishes nothing, every later pass returns at once, and the host reports the error at its next call.
+struct FusedEpi {
+    int enabled;
+    unsigned int *rb_arrive;  // per row block: column splits finished (returns to 0 by the end of the pass)
+    double *rb_sums;          // nrb x K
+    unsigned int *done;       // row blocks finished
+    const float *M; const int *mat; float *B;
+    float *res_out_block;     // this rank's block of the next exchange buffer (npeers == 0)
+    double *block_sums;
+    int npeers;
+    float *peer_out[16];
+    double *peer_sums[16];
+    unsigned long long *peer_flag[16];
+    unsigned long long seq;
+    unsigned long long *flags;       // own flag array; [16] = abort marker
+    unsigned long long *host_abort;  // host-mapped copy of the abort marker (may be null)
+    int G;
+    unsigned long long wait_seq;     // 0: nothing to wait for
+    unsigned long long timeout_ns;
+};
 
 template <int K>
-__global__ void __launch_bounds__((TmaCfg<K>::NCW + 1) * 32, 1)
-k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmRes) {
+__global__ void __launch_bounds__((TmaCfg<K>::NCW + 3) * 32, 1)
+k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ FusedEpi E) {
     constexpr int NST = tma_nstage<K>();
     constexpr int STAGE_F = tma_stage_bytes<K>() / 4; // floats per stage
     constexpr int RW = TmaCfg<K>::RW, NCW = TmaCfg<K>::NCW, T_ROWS = RW * NCW, T_COLS = TmaCfg<K>::COLS;
@@ -263,7 +307,11 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     float *stages = reinterpret_cast<float *>(g_smem);
     uint64_t *full = reinterpret_cast<uint64_t *>(g_smem + (size_t)NST * tma_stage_bytes<K>());
     uint64_t *empty = full + NST;
+    float *s_out = reinterpret_cast<float *>(empty + NST + 2);              // 2 x T_ROWS x K sums of a block (single split), double-buffered
+    double *s_red = reinterpret_cast<double *>(s_out + 2 * tma_rows<K>() * K); // 2 KB: ordered reductions
+    int *s_flag = reinterpret_cast<int *>(empty + NST);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (E.enabled && *reinterpret_cast<volatile unsigned long long *>(E.flags + 16) != 0ull) return; // an earlier pass gave up on a peer
     if (tid == 0) {
         for (int i = 0; i < NST; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -271,12 +319,137 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     __syncthreads();
     const int nitems = P.nrb * P.nsplit;
     uint32_t it = 0; // global step counter: stage = it % NST, phase = (it / NST) & 1
-    if (warp == NCW) {
+    if (warp > NCW) {
+        // ------------------------------- epilogue warps (64 threads) -------------------------------
+        // They take over each finished item from the consumers (named barriers 2/3: "item done", 4/5: "buffer free"), so
+        // the streaming never waits for an epilogue; only the last epilogue of a CTA is exposed.
+        if (!E.enabled) return;
+        const int et = tid - (NCW + 1) * 32, ewarp = et >> 5;
+        auto esync = [&]() { asm volatile("bar.sync 1, 64;" ::: "memory"); };
+        unsigned nitem_done = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x, nitem_done++) {
+            const int rb = item / P.nsplit;
+            const int buf = (int)(nitem_done & 1u);
+            DZ_ASSERT(rb >= 0 && rb < P.nrb);
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + buf), "n"(NCW * 32 + 64) : "memory"); // the consumers have written this item's sums
+            bool last = true;
+            if (P.nsplit > 1) {
+                if (et == 0) {
+                    // release: the consumers' partial rows (ordered before this thread by the named barrier) become visible
+                    // device-wide before the arrival is counted -- barrier + one fence + atomic, the usual semaphore pattern
+                    __threadfence();
+                    const unsigned old = atomicAdd(&E.rb_arrive[rb], 1u);
+                    const int l = (old == (unsigned)P.nsplit - 1u);
+                    if (l) E.rb_arrive[rb] = 0u;
+                    *s_flag = l;
+                }
+                esync();
+                last = *s_flag != 0;
+                esync();
+                if (last) __threadfence();
+            }
+            if (last) {
+                double loc[K];
+#pragma unroll
+                for (int k = 0; k < K; k++) loc[k] = 0.0;
+                const int row = rb * T_ROWS + et;
+                if (et < T_ROWS && row < P.nloc) {
+                    float b[K], Bv[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) Bv[k] = E.B[(size_t)k * P.n + row]; // issued first: independent of everything below
+                    DZ_ASSERT(E.mat[row] >= 0 && row < P.n);
+                    const float *Mp = E.M + (size_t)E.mat[row] * K * K;
+                    if (P.nsplit == 1) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) b[k] = s_out[buf * (T_ROWS * K) + et * K + k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; k++) b[k] = 0.0f;
+                        for (int sp = 0; sp < P.nsplit; sp++) { // fixed order: the result does not depend on which CTA came last
+                            const float *src = P.partial + ((size_t)sp * P.nloc + row) * K;
+#pragma unroll
+                            for (int k = 0; k < K; k++) b[k] += __ldcg(src + k);
+                        }
+                    }
+                    float y[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        // result = reflectionmatrix[i] * patchrowvec  (column-major K x K)            Lightning.h:212
+                        float v = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < K; j++) v = fmaf(__ldg(Mp + j * K + k), b[j], v);
+                        y[k] = v;
+                        loc[k] = (double)v;
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        if (E.npeers > 0) {
+                            for (int g = 0; g < E.npeers; g++) E.peer_out[g][(size_t)k * P.n + row] = y[k]; // NVLink stores into every rank's buffer
+                        } else {
+                            E.res_out_block[(size_t)k * P.n + row] = y[k];                   // residualvector[j][i] = result[j]
+                        }
+                        E.B[(size_t)k * P.n + row] = Bv[k] + y[k];                           // lightningvalues += residual   :221-223
+                    }
+                    if (E.npeers > 0) __threadfence_system(); else __threadfence();
+                }
+                // band sums of the block: lanes -> warps -> block, always in index order
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    double v = loc[k];
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0) s_red[ewarp * K + k] = v;
+                }
+                esync();
+                if (et < K) {
+                    E.rb_sums[(size_t)rb * K + et] = s_red[et] + s_red[K + et];
+                    __threadfence();
+                }
+                esync();
+                if (et == 0) *s_flag = (atomicAdd(E.done, 1u) == (unsigned)P.nrb - 1u);
+                esync();
+                const bool final_block = *s_flag != 0;
+                esync();
+                if (final_block) {
+                    // the pass's last row block: total the band sums in block order (a fixed two-level order) and publish
+                    __threadfence();
+                    constexpr int NCH = (256 / K) < 32 ? (256 / K) : 32; // chunks of consecutive row blocks per band (NCH x K doubles fit s_red)
+                    const int per = (P.nrb + NCH - 1) / NCH;
+                    for (int t = et; t < NCH * K; t += 64) {
+                        const int k = t % K, c = t / K;
+                        double v = 0.0;
+                        const volatile double *rs = E.rb_sums;
+                        for (int b2 = c * per; b2 < min(P.nrb, (c + 1) * per); b2++) v += rs[(size_t)b2 * K + k];
+                        s_red[c * K + k] = v;
+                    }
+                    esync();
+                    const bool aborted = *reinterpret_cast<volatile unsigned long long *>(E.flags + 16) != 0ull;
+                    if (et < K) {
+                        double v = 0.0;
+                        for (int c = 0; c < NCH; c++) v += s_red[c * K + et];
+                        if (E.npeers > 0) { for (int g = 0; g < E.npeers; g++) E.peer_sums[g][et] = v; }
+                        else E.block_sums[et] = v;
+                    }
+                    if (et == 0) *E.done = 0u;
+                    if (E.npeers > 0) {
+                        __threadfence_system();
+                        esync();
+                        if (et < E.npeers && !aborted) {
+                            // release: every store of this pass (fenced by its CTA before it arrived on `done`) precedes the flag
+                            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(E.peer_flag[et]), "l"(E.seq) : "memory");
+                        }
+                    }
+                    esync();
+                }
+            }
+            asm volatile("bar.arrive %0, %1;" ::"r"(4 + buf), "n"(NCW * 32 + 64) : "memory"); // this buffer may be refilled
+        }
+    } else if (warp == NCW) {
         // ------------------------------- producer -------------------------------
         // one elected lane issues two tiled TMA loads per stage: the T_ROWS x 128 block of F and the K x 128 block
         // of the residual bands (tiles never straddle an exchange block: n is a multiple of 256 when G > 1, and a
         // single block's tail beyond n is zero-filled by the TMA unit)
         if (lane == 0) {
+            unsigned ready = (E.enabled && E.wait_seq != 0ull) ? 0u : 0xffffffffu; // ranks whose block of the previous pass is known to be here
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int rb = item / P.nsplit, split = item - rb * P.nsplit;
                 const int c_begin = split * P.colw;
@@ -291,12 +464,32 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                     mbar_expect_tx(&full[st], (uint32_t)tma_stage_bytes<K>());
                     tma_load_2d(sf, &tmF, col0, row0, &full[st]);
                     const int g = col0 / P.n, jl = col0 - g * P.n;
+                    DZ_ASSERT(g >= 0 && g < 32 && col0 < P.ncols && row0 < P.nloc + T_ROWS);
+                    if (!((ready >> g) & 1u)) {
+                        unsigned long long t0, t1, v;
+                        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+                        while (true) {
+                            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(E.flags + g) : "memory");
+                            if (v >= E.wait_seq) break;
+                            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                            if (t1 - t0 > E.timeout_ns) {
+                                E.flags[16] = E.seq;
+                                if (E.host_abort) *reinterpret_cast<volatile unsigned long long *>(E.host_abort) = E.seq;
+                                __threadfence_system();
+                                break;
+                            }
+                            __nanosleep(100);
+                        }
+                        ready |= 1u << g;
+                        asm volatile("fence.proxy.async;" ::: "memory"); // the peer's stores, seen by the acquire above, before the TMA reads below
+                    }
                     tma_load_3d(sf + T_ROWS * T_COLS, &tmRes, jl, 0, g, &full[st]);
                 }
             }
         }
     } else {
         // ------------------------------- consumers ------------------------------
+        unsigned nitem_done = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int rb = item / P.nsplit, split = item - rb * P.nsplit;
             const int c_begin = split * P.colw;
@@ -344,17 +537,26 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
                     acc[r][k] = v;
                 }
+            // hand the block's sums to the epilogue warps (double-buffered: the consumers go straight on to the next item)
+            const int buf = (int)(nitem_done & 1u);
+            if (E.enabled && nitem_done >= 2u) asm volatile("bar.sync %0, %1;" ::"r"(4 + buf), "n"(NCW * 32 + 64) : "memory"); // epilogue of item - 2 has let go of this buffer
             if (lane == 0) {
 #pragma unroll
                 for (int r = 0; r < RW; r++) {
                     int row = row_base + r;
-                    if (row < P.nloc) {
+                    if (E.enabled && P.nsplit == 1) {
+                        float *dst = s_out + buf * (T_ROWS * K) + (warp * RW + r) * K;
+#pragma unroll
+                        for (int k = 0; k < K; k++) dst[k] = acc[r][k];
+                    } else if (row < P.nloc) {
                         float *dst = P.partial + ((size_t)split * P.nloc + row) * K;
 #pragma unroll
                         for (int k = 0; k < K; k++) dst[k] = acc[r][k];
                     }
                 }
             }
+            if (E.enabled) asm volatile("bar.arrive %0, %1;" ::"r"(2 + buf), "n"(NCW * 32 + 64) : "memory");
+            nitem_done++;
         }
     }
 }
@@ -376,6 +578,7 @@ struct EpiParams {
     double *peer_sums[16];
     unsigned long long *peer_flag[16];
     unsigned long long seq;
+    const unsigned long long *abort_marker; // flag word 16 of this rank (null: single GPU)
 };
 
 template <int K>
@@ -441,7 +644,8 @@ __global__ void __launch_bounds__(256) k_gather_epilogue(EpiParams P) {
         if (P.npeers > 0) {
             __threadfence_system();
             __syncthreads();
-            if (tid < P.npeers) {
+            const bool aborted = P.abort_marker && *reinterpret_cast<const volatile unsigned long long *>(P.abort_marker) != 0ull;
+            if (tid < P.npeers && !aborted) {
                 // release: every store of this kernel (fenced by each CTA before it arrived on `done`) precedes the flag
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.peer_flag[tid]), "l"(P.seq) : "memory");
             }
@@ -449,9 +653,10 @@ __global__ void __launch_bounds__(256) k_gather_epilogue(EpiParams P) {
     }
 }
 
-// waits until every rank's block of pass `seq` has arrived in this rank's buffer (flag[g] >= seq for all g); gives up
-// after ~2 s so that a dead peer turns into an error instead of a hung GPU
-__global__ void k_wait_flags(unsigned long long *flags, int G, unsigned long long seq) {
+// waits until every rank's block of pass `seq` has arrived in this rank's buffer (flag[g] >= seq for all g).  A peer that does
+// not show up within timeout_ns turns into an error instead of a hung GPU: the abort markers are set (flag word 16 and the
+// host-mapped word), the kernels of later passes return at once and nothing more is published to the peers.
+__global__ void k_wait_flags(unsigned long long *flags, int G, unsigned long long seq, unsigned long long timeout_ns, unsigned long long *host_abort) {
     const int g = threadIdx.x;
     if (g >= G) return;
     unsigned long long t0;
@@ -460,9 +665,15 @@ __global__ void k_wait_flags(unsigned long long *flags, int G, unsigned long lon
         unsigned long long v;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + g) : "memory");
         if (v >= seq) break;
+        if (*reinterpret_cast<volatile unsigned long long *>(flags + 16) != 0ull) break;
         unsigned long long t1;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 2000000000ull) { flags[16] = seq; break; }
+        if (t1 - t0 > timeout_ns) {
+            flags[16] = seq;
+            if (host_abort) *reinterpret_cast<volatile unsigned long long *>(host_abort) = seq;
+            __threadfence_system();
+            break;
+        }
         __nanosleep(200);
     }
 }
@@ -481,9 +692,15 @@ static int launch_partial(daisy_solver *s, const GatherParams &P) {
     return DAISY_OK;
 }
 
+// wait_seq != 0 (fused exchange): the blocks of pass wait_seq must have arrived before the residual is read.  The fused TMA
+// kernel waits by itself, block by block; the other kernels get a k_wait_flags launch in front.
 template <int K>
-static int launch_pass_K(daisy_solver *s) {
+static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
     daisy_ctx *c = s->ctx;
+    if (wait_seq != 0ull && !s->fused_epi) {
+        k_wait_flags<<<1, 32, 0, c->stream>>>(s->d_flags, s->G, wait_seq, s->timeout_ns, s->d_abort_host);
+        DZ_CUDA(cudaGetLastError());
+    }
     GatherParams P;
     P.F = c->d_F; P.ldF = c->ldF; P.nloc = s->nloc; P.ncols = s->G * s->n; P.n = s->n;
     P.res = s->d_res[s->cur]; P.bstride = s->bstride; P.partial = s->d_partial;
@@ -506,15 +723,36 @@ static int launch_pass_K(daisy_solver *s) {
         rc = DAISY_OK;
     } else if (s->use_tma) {
         constexpr int NST = tma_nstage<K>();
-        size_t smem = (size_t)NST * tma_stage_bytes<K>() + 2 * NST * sizeof(uint64_t);
+        size_t smem = (size_t)NST * tma_stage_bytes<K>() + 2 * NST * sizeof(uint64_t) + tma_epi_bytes<K>();
         static bool attr_done = false;
         if (!attr_done) {
             DZ_CUDA(cudaFuncSetAttribute(k_gather_tma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_done = true;
         }
         P.nrb = (s->nloc + tma_rows<K>() - 1) / tma_rows<K>();
-        k_gather_tma<K><<<s->grid, (TmaCfg<K>::NCW + 1) * 32, smem, c->stream>>>(P, s->tmF, s->tmRes[s->cur]);
+        FusedEpi F;
+        memset(&F, 0, sizeof(F));
+        F.enabled = s->fused_epi ? 1 : 0;
+        if (s->fused_epi) {
+            float *next = s->d_res[s->cur ^ 1] + (size_t)s->rank * s->bstride;
+            F.rb_arrive = s->d_rb_arrive; F.rb_sums = s->d_rb_sums; F.done = s->d_done;
+            F.M = s->d_M; F.mat = s->d_mat; F.B = s->d_B;
+            F.res_out_block = next; F.block_sums = reinterpret_cast<double *>(next + s->sums_off);
+            F.seq = s->seq; F.flags = s->d_flags; F.host_abort = s->d_abort_host; F.G = s->G;
+            F.wait_seq = wait_seq; F.timeout_ns = s->timeout_ns;
+            if (s->fused) {
+                F.npeers = s->G;
+                for (int g = 0; g < s->G; g++) {
+                    float *blk = s->peer_res[s->cur ^ 1][g] + (size_t)s->rank * s->bstride;
+                    F.peer_out[g] = blk;
+                    F.peer_sums[g] = reinterpret_cast<double *>(blk + s->sums_off);
+                    F.peer_flag[g] = s->peer_flags[g] + s->rank;
+                }
+            }
+        }
+        k_gather_tma<K><<<s->grid, (TmaCfg<K>::NCW + 3) * 32, smem, c->stream>>>(P, s->tmF, s->tmRes[s->cur], F);
         DZ_CUDA(cudaGetLastError());
+        if (s->fused_epi) return DAISY_OK; // the whole pass was that one launch
         rc = DAISY_OK;
     } else if constexpr (K <= 9) {
         rc = (s->R == 8) ? launch_partial<K, 8>(s, P) : launch_partial<K, 4>(s, P);
@@ -527,7 +765,7 @@ static int launch_pass_K(daisy_solver *s) {
     E.partial = s->d_partial; E.nsplit = s->nsplit; E.nloc = s->nloc; E.n = s->n;
     E.M = s->d_M; E.mat = s->d_mat; E.res_out_block = next; E.B = s->d_B;
     E.cta_sums = s->d_cta_sums; E.block_sums = reinterpret_cast<double *>(next + s->sums_off); E.done = s->d_done;
-    E.npeers = 0; E.seq = s->seq;
+    E.npeers = 0; E.seq = s->seq; E.abort_marker = s->fused ? s->d_flags + 16 : nullptr;
     if (s->fused) {
         E.npeers = s->G;
         for (int g = 0; g < s->G; g++) {
@@ -545,13 +783,13 @@ static int launch_pass_K(daisy_solver *s) {
     return DAISY_OK;
 }
 
-static int launch_pass(daisy_solver *s) {
+static int launch_pass(daisy_solver *s, unsigned long long wait_seq = 0ull) {
     switch (s->Kp) {
-    case 1: return launch_pass_K<1>(s);
-    case 3: return launch_pass_K<3>(s);
-    case 9: return launch_pass_K<9>(s);
-    case 16: return launch_pass_K<16>(s);
-    case 32: return launch_pass_K<32>(s);
+    case 1: return launch_pass_K<1>(s, wait_seq);
+    case 3: return launch_pass_K<3>(s, wait_seq);
+    case 9: return launch_pass_K<9>(s, wait_seq);
+    case 16: return launch_pass_K<16>(s, wait_seq);
+    case 32: return launch_pass_K<32>(s, wait_seq);
     }
     daisy_set_error("unsupported padded band count %d", s->Kp);
     return DAISY_E_INVALID;
@@ -626,12 +864,19 @@ static void plan(daisy_solver *s) {
     s->use_tma = !(env && strcmp(env, "ldg") == 0);
     // wide band counts run on the tensor cores unless DAISY_GATHER=fp32 (or ldg) asks for the CUDA-core kernels
     s->use_mma = s->use_tma && s->Kp >= 16 && !(env && strcmp(env, "fp32") == 0);
+    {
+        const char *e2 = getenv("DAISY_GATHER_EPI"); // "split": keep the separate epilogue kernel (A/B switch)
+        s->fused_epi = s->use_tma && !s->use_mma && !(e2 && strcmp(e2, "split") == 0);
+    }
     int Rs[2];
     if (s->use_mma) { Rs[0] = Rs[1] = MM_ROWS / G_WARPS; } // 128-row tiles
     else if (s->use_tma) { Rs[0] = Rs[1] = (s->Kp == 32 ? 4 : 8); } // rows per block / G_WARPS: 64-row tiles, 32-row for K=32
     else if (s->Kp <= 9) { Rs[0] = 8; Rs[1] = 4; } else { Rs[0] = 2; Rs[1] = 4; }
     int ncols = s->G * s->n;
-    int maxsplit = (ncols + 4 * G_TC - 1) / (4 * G_TC); // keep at least 2048 columns per item
+    // keep at least 2048 columns per item -- 1024 with the fused epilogue, where a split costs one partial row per block and no
+    // extra launch: small matrices (the reference's own scenes: ~120 row blocks) then fill the 148 SMs evenly
+    const int mincols = s->fused_epi ? 2 * G_TC : 4 * G_TC;
+    int maxsplit = (ncols + mincols - 1) / mincols;
     if (maxsplit < 1) maxsplit = 1;
     if (maxsplit > 32) maxsplit = 32;
     double best = -1.0;
@@ -656,7 +901,7 @@ static int padded_K(int K) { return K <= 1 ? 1 : K <= 3 ? 3 : K <= 9 ? 9 : K <= 
 
 static void free_solver(daisy_solver *s) {
     if (!s) return;
-    if (s->fused)
+    if (s->fused && s->peers_ipc)
         for (int g = 0; g < s->G; g++) {
             if (g == s->rank) continue;
             if (s->peer_res[0][g]) cudaIpcCloseMemHandle(s->peer_res[0][g]);
@@ -666,6 +911,8 @@ static void free_solver(daisy_solver *s) {
     cudaFree(s->d_flags);
     cudaFree(s->d_res[0]); cudaFree(s->d_res[1]); cudaFree(s->d_B); cudaFree(s->d_E); cudaFree(s->d_M); cudaFree(s->d_mat);
     cudaFree(s->d_partial); cudaFree(s->d_cta_sums); cudaFree(s->d_done); cudaFree(s->d_split);
+    cudaFree(s->d_rb_arrive); cudaFree(s->d_rb_sums);
+    if (s->h_abort) cudaFreeHost(s->h_abort);
     if (s->e0) cudaEventDestroy(s->e0);
     if (s->e1) cudaEventDestroy(s->e1);
     delete s;
@@ -723,6 +970,19 @@ extern "C" int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const 
     SC(cudaMalloc(&s->d_cta_sums, sizeof(double) * 148 * s->Kp));
     SC(cudaMalloc(&s->d_done, sizeof(unsigned int)));
     SC(cudaMemset(s->d_done, 0, sizeof(unsigned int)));
+    {
+        const int trows = (s->Kp == 32) ? 32 : 64; // = tma_rows<Kp>()
+        s->nrb_tma = (s->nloc + trows - 1) / trows;
+        if (s->nrb_tma < 1) s->nrb_tma = 1;
+        SC(cudaMalloc(&s->d_rb_arrive, sizeof(unsigned int) * (size_t)s->nrb_tma));
+        SC(cudaMemset(s->d_rb_arrive, 0, sizeof(unsigned int) * (size_t)s->nrb_tma));
+        SC(cudaMalloc(&s->d_rb_sums, sizeof(double) * (size_t)s->nrb_tma * s->Kp));
+        SC(cudaHostAlloc(reinterpret_cast<void **>(&s->h_abort), sizeof(unsigned long long), cudaHostAllocMapped));
+        *s->h_abort = 0ull;
+        SC(cudaHostGetDevicePointer(reinterpret_cast<void **>(&s->d_abort_host), s->h_abort, 0));
+        const char *e = getenv("DAISY_EXCHANGE_TIMEOUT_MS");
+        if (e && atof(e) > 0.0) s->timeout_ns = (unsigned long long)(atof(e) * 1e6);
+    }
     SC(cudaMalloc(&s->d_flags, sizeof(unsigned long long) * 17));
     SC(cudaMemset(s->d_flags, 0, sizeof(unsigned long long) * 17));
     SC(cudaMemset(s->d_res[0], 0, exb));
@@ -747,6 +1007,9 @@ extern "C" int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const 
         if (s->nloc > 0) SC(cudaMemcpy(s->d_mat, mat_idx + s->row0, sizeof(int) * (size_t)s->nloc, cudaMemcpyHostToDevice));
     }
 #undef SC
+    // the set-up above used synchronous copies and legacy-stream memsets; the solver's kernels run on ctx->stream, which may be
+    // a non-blocking stream (daisy_ctx_set_stream): make sure everything has landed before anything is enqueued there
+    { cudaError_t e_ = cudaDeviceSynchronize(); if (e_ != cudaSuccess) { daisy_set_error("daisy_solver_create: %s", cudaGetErrorString(e_)); free_solver(s); return DAISY_E_CUDA; } }
     compute_sums_from_host(s, E);
     s->e_sums = s->sums;
     *out = s;
@@ -766,7 +1029,15 @@ extern "C" int daisy_solver_reset(daisy_solver *s) {
     cudaStream_t st = s->ctx->stream;
     size_t exb = sizeof(float) * (size_t)s->G * s->bstride;
     // fused exchange: a slower rank may still be storing its block of the last pass into this rank's buffers
-    if (s->fused && s->seq > 0) k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq);
+    if (s->fused && s->seq > 0) {
+        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq, s->timeout_ns, s->d_abort_host);
+        DZ_CUDA(cudaGetLastError());
+    }
+    // a pass that gave up on a peer leaves its counters half way and the abort markers set: start clean
+    DZ_CUDA(cudaMemsetAsync(s->d_done, 0, sizeof(unsigned int), st));
+    DZ_CUDA(cudaMemsetAsync(s->d_rb_arrive, 0, sizeof(unsigned int) * (size_t)s->nrb_tma, st));
+    DZ_CUDA(cudaMemsetAsync(s->d_flags + 16, 0, sizeof(unsigned long long), st));
+    if (s->h_abort) *s->h_abort = 0ull;
     // residualvector = emission; lightningvalues = emission                                 Lightning.h:159-165
     s->cur = 0;
     DZ_CUDA(cudaMemcpyAsync(s->d_res[0], s->d_E, exb, cudaMemcpyDeviceToDevice, st));
@@ -780,6 +1051,7 @@ extern "C" int daisy_solver_reset(daisy_solver *s) {
 
 extern "C" int daisy_solver_step_local(daisy_solver *s) {
     DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_step_local: null solver");
+    DzRange range_("gather pass");
     DZ_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
     DZ_CUDA(cudaEventRecord(s->e0, st));
@@ -802,7 +1074,7 @@ static int fetch_sums(daisy_solver *s) {
     cudaStream_t st = s->ctx->stream;
     unsigned long long timed_out = 0;
     if (s->fused) {
-        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq); // every rank's block of the last pass has landed
+        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq, s->timeout_ns, s->d_abort_host); // every rank's block of the last pass has landed
         DZ_CUDA(cudaGetLastError());
         DZ_CUDA(cudaMemcpyAsync(&timed_out, s->d_flags + 16, sizeof(timed_out), cudaMemcpyDeviceToHost, st));
     }
@@ -811,7 +1083,11 @@ static int fetch_sums(daisy_solver *s) {
         DZ_CUDA(cudaMemcpyAsync(&tails[(size_t)g * s->Kp], s->d_res[s->cur] + (size_t)g * s->bstride + s->sums_off,
                                 sizeof(double) * s->Kp, cudaMemcpyDeviceToHost, st));
     DZ_CUDA(cudaStreamSynchronize(st));
-    if (timed_out) { daisy_set_error("fused exchange: a peer's block of pass %llu did not arrive within 2 s", timed_out); return DAISY_E_STATE; }
+    if (timed_out) {
+        daisy_set_error("fused exchange: a peer's block of pass %llu did not arrive within %.1f s; the solver is stopped until daisy_solver_reset",
+                        timed_out, (double)s->timeout_ns * 1e-9);
+        return DAISY_E_STATE;
+    }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, s->e0, s->e1) == cudaSuccess) s->last_ms = ms;
     s->sums.assign(s->K, 0.0);
@@ -876,6 +1152,76 @@ extern "C" int daisy_solver_set_peers(daisy_solver *s, const void *handles, int 
         s->peer_res[0][g] = (float *)p0; s->peer_res[1][g] = (float *)p1; s->peer_flags[g] = (unsigned long long *)p2;
     }
     s->fused = true;
+    s->peers_ipc = true;
+    return DAISY_OK;
+}
+
+int dz_solver_get_buffers(daisy_solver *s, float **res0, float **res1, unsigned long long **flags) {
+    *res0 = s->d_res[0]; *res1 = s->d_res[1]; *flags = s->d_flags;
+    return DAISY_OK;
+}
+
+int dz_solver_set_peer_pointers(daisy_solver *s, float *const *res0, float *const *res1, unsigned long long *const *flags, int nranks) {
+    DZ_REQUIRE(s && res0 && res1 && flags, DAISY_E_INVALID, "solver_set_peer_pointers: null argument");
+    DZ_REQUIRE(nranks == s->G && nranks <= 16, DAISY_E_INVALID, "solver_set_peer_pointers: nranks must match the partition (<= 16)");
+    DZ_REQUIRE(!s->fused, DAISY_E_STATE, "solver_set_peer_pointers: peers already set");
+    for (int g = 0; g < nranks; g++) { s->peer_res[0][g] = res0[g]; s->peer_res[1][g] = res1[g]; s->peer_flags[g] = flags[g]; }
+    s->fused = true;
+    s->peers_ipc = false;
+    return DAISY_OK;
+}
+
+// ---- slice upload for the fused exchange: every rank uploads ONLY its own rows of B and of the residual; the residual slice
+// (with its band sums) is then handed to every rank over NVLink exactly like the output of a pass -- block `rank` of every
+// rank's next buffer, flag[rank] = new pass number -- so the next pass finds the whole vector in place.
+__global__ void k_raise_flags(int npeers, unsigned long long seq, const unsigned long long *abort_marker, unsigned long long *f0, unsigned long long *f1,
+                              unsigned long long *f2, unsigned long long *f3, unsigned long long *f4, unsigned long long *f5, unsigned long long *f6,
+                              unsigned long long *f7, unsigned long long *f8, unsigned long long *f9, unsigned long long *f10, unsigned long long *f11,
+                              unsigned long long *f12, unsigned long long *f13, unsigned long long *f14, unsigned long long *f15) {
+    unsigned long long *f[16] = { f0, f1, f2, f3, f4, f5, f6, f7, f8, f9, f10, f11, f12, f13, f14, f15 };
+    const int g = threadIdx.x;
+    if (g >= npeers || *reinterpret_cast<const volatile unsigned long long *>(abort_marker) != 0ull) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f[g]), "l"(seq) : "memory");
+}
+
+extern "C" int daisy_solver_write_slices(daisy_solver *s, const float *B_local, const float *residual_local) {
+    DZ_REQUIRE(s && B_local && residual_local, DAISY_E_INVALID, "daisy_solver_write_slices: null argument");
+    DZ_REQUIRE(s->G == 1 || s->fused, DAISY_E_STATE, "daisy_solver_write_slices: a partitioned solver needs the fused exchange (daisy_solver_set_peers)");
+    DZ_CUDA(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->stream;
+    if (s->G == 1) return daisy_solver_write(s, B_local, residual_local);
+    // every rank has finished the last pass (and with it all reads of the buffer about to be overwritten)
+    if (s->seq > 0) {
+        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq, s->timeout_ns, s->d_abort_host);
+        DZ_CUDA(cudaGetLastError());
+    }
+    const int nxt = s->cur ^ 1;
+    float *own = s->d_res[nxt] + (size_t)s->rank * s->bstride;
+    if (s->nloc > 0) {
+        DZ_CUDA(cudaMemcpy2DAsync(s->d_B, sizeof(float) * s->n, B_local, sizeof(float) * s->nloc, sizeof(float) * s->nloc, s->K, cudaMemcpyHostToDevice, st));
+        DZ_CUDA(cudaMemcpy2DAsync(own, sizeof(float) * s->n, residual_local, sizeof(float) * s->nloc, sizeof(float) * s->nloc, s->K, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<double> tail((size_t)s->Kp, 0.0);
+    for (int k = 0; k < s->K; k++) {
+        double v = 0.0;
+        for (int p = 0; p < s->nloc; p++) v += (double)residual_local[(size_t)k * s->nloc + p];
+        tail[(size_t)k] = v;
+    }
+    DZ_CUDA(cudaMemcpyAsync(own + s->sums_off, tail.data(), sizeof(double) * s->Kp, cudaMemcpyHostToDevice, st));
+    DZ_CUDA(cudaStreamSynchronize(st)); // `tail` is pageable host memory
+    for (int g = 0; g < s->G; g++) {
+        if (g == s->rank) continue;
+        DZ_CUDA(cudaMemcpyAsync(s->peer_res[nxt][g] + (size_t)s->rank * s->bstride, own, sizeof(float) * (size_t)s->bstride, cudaMemcpyDeviceToDevice, st));
+    }
+    s->seq++;
+    unsigned long long *f[16];
+    for (int g = 0; g < 16; g++) f[g] = (g < s->G) ? s->peer_flags[g] + s->rank : nullptr;
+    k_raise_flags<<<1, 32, 0, st>>>(s->G, s->seq, s->d_flags + 16, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9], f[10], f[11], f[12],
+                                    f[13], f[14], f[15]);
+    DZ_CUDA(cudaGetLastError());
+    s->cur = nxt;
+    s->sums_valid = false;
     return DAISY_OK;
 }
 
@@ -884,15 +1230,18 @@ extern "C" int daisy_solver_set_peers(daisy_solver *s, const void *handles, int 
 extern "C" int daisy_solver_step_fused(daisy_solver *s, double *band_sums) {
     DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_step_fused: null solver");
     DZ_REQUIRE(s->fused, DAISY_E_STATE, "daisy_solver_step_fused: call daisy_solver_set_peers first");
+    DzRange range_("gather pass + fused exchange");
     DZ_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
-    DZ_CUDA(cudaEventRecord(s->e0, st));
-    if (s->seq > 0) {
-        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq);
-        DZ_CUDA(cudaGetLastError());
+    if (s->h_abort && *reinterpret_cast<volatile unsigned long long *>(s->h_abort) != 0ull) {
+        daisy_set_error("fused exchange: a peer's block of pass %llu did not arrive within %.1f s; the solver is stopped until daisy_solver_reset",
+                        *s->h_abort, (double)s->timeout_ns * 1e-9);
+        return DAISY_E_STATE;
     }
+    DZ_CUDA(cudaEventRecord(s->e0, st));
+    const unsigned long long wait_seq = s->seq; // the blocks of the previous pass (0: first pass, nothing to wait for)
     s->seq++;
-    int rc = launch_pass(s);
+    int rc = launch_pass(s, wait_seq);
     if (rc) return rc;
     DZ_CUDA(cudaEventRecord(s->e1, st));
     return daisy_solver_step_finish(s, band_sums);
@@ -910,7 +1259,8 @@ static bool unconverged(const daisy_solver *s, double threshold, int per_band) {
 
 extern "C" int daisy_solver_converge(daisy_solver *s, double threshold, int per_band, int max_passes, int *passes_out) {
     DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_converge: null solver");
-    DZ_REQUIRE(s->G == 1, DAISY_E_STATE, "daisy_solver_converge: partitioned solver is driven by the host exchange loop");
+    DZ_REQUIRE(s->G == 1, DAISY_E_STATE, "daisy_solver_converge: partitioned solver is driven by the host exchange loop (or daisy_group_solver_converge)");
+    DzRange range_("daisy_solver_converge");
     int done = 0;
     std::vector<double> tmp(s->K);
     if (!s->sums_valid) { int rc = fetch_sums(s); if (rc) return rc; }
@@ -965,7 +1315,10 @@ extern "C" int daisy_solver_write_partitioned(daisy_solver *s, const float *B_lo
     DZ_REQUIRE(s && B_local && residual_full, DAISY_E_INVALID, "daisy_solver_write_partitioned: null argument");
     DZ_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
-    if (s->fused && s->seq > 0) k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq); // peers' stores of the last pass have landed
+    if (s->fused && s->seq > 0) { // peers' stores of the last pass have landed
+        k_wait_flags<<<1, 32, 0, st>>>(s->d_flags, s->G, s->seq, s->timeout_ns, s->d_abort_host);
+        DZ_CUDA(cudaGetLastError());
+    }
     if (s->nloc > 0)
         DZ_CUDA(cudaMemcpy2DAsync(s->d_B, sizeof(float) * s->n, B_local, sizeof(float) * s->nloc, sizeof(float) * s->nloc, s->K, cudaMemcpyHostToDevice, st));
     for (int g = 0; g < s->G; g++) {
@@ -978,6 +1331,16 @@ extern "C" int daisy_solver_write_partitioned(daisy_solver *s, const float *B_lo
     compute_sums_from_host(s, residual_full);
     s->sums_valid = true;
     return DAISY_OK;
+}
+
+// kernels one pass launches in this solver's configuration (the benchmark reports it)
+extern "C" int daisy_solver_launches_per_pass(daisy_solver *s) {
+    if (!s) return DAISY_E_INVALID;
+    if (s->fused_epi) return 1;                         // k_gather_tma with the epilogue and the exchange wait inside
+    int n = 2;                                          // streaming kernel + k_gather_epilogue
+    if (s->use_mma) n += 1;                             // k_split_residual
+    if (s->fused) n += 1;                               // k_wait_flags
+    return n;
 }
 
 extern "C" int daisy_solver_last_step_ms(daisy_solver *s, double *ms) {

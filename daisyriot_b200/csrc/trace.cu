@@ -10,7 +10,6 @@
 // records the picking code wants) leaves the device.
 #include "daisy_common.cuh"
 #include "closest.cuh"
-#include <nvtx3/nvToolsExt.h>
 
 // per-vertex colour: sum of get_color_of_patch over trianglesPerVertex[v] in ascending triangle order (MeshS.cpp:107-109
 // pushes them in that order), divided component-wise by the count (Drawer.cpp:169-180)

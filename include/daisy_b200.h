@@ -165,6 +165,8 @@ int daisy_solver_exchange_info(daisy_solver *s, void **d_next_buffer, int64_t *b
 int daisy_solver_step_finish(daisy_solver *s, double *band_sums);
 /* timing of the last step: device milliseconds of the gather kernel (CUDA events on the context's stream) */
 int daisy_solver_last_step_ms(daisy_solver *s, double *ms);
+/* kernels one pass launches in this solver's configuration: 1 for K <= 9 (streaming, epilogue and exchange wait in one kernel) */
+int daisy_solver_launches_per_pass(daisy_solver *s);
 
 /* Fused exchange (replaces the NCCL all-gather of the loop above when all ranks sit in one NVLink domain):
  *   daisy_solver_ipc_handles: 3 x 64-byte CUDA-IPC handles of this rank's two exchange buffers and its flag array
@@ -177,6 +179,47 @@ int daisy_solver_write_partitioned(daisy_solver *s, const float *B_local, const 
 int daisy_solver_ipc_handles(daisy_solver *s, void *handles192);
 int daisy_solver_set_peers(daisy_solver *s, const void *handles, int nranks);
 int daisy_solver_step_fused(daisy_solver *s, double *band_sums);
+
+
+/* upload only this rank's rows: B_local and residual_local are K x (row1-row0).  With more than one rank (fused exchange set
+ * up) the residual slice and its band sums are handed to every rank over NVLink like the output of a pass, so the next
+ * daisy_solver_step_fused finds the whole vector in place.  Single rank: same as daisy_solver_write. */
+int daisy_solver_write_slices(daisy_solver *s, const float *B_local, const float *residual_local);
+
+/* ---- several GPUs behind ONE host process ---------------------------------------------------------------------------------
+ * The reference is a single process (main.cpp:97-113: MeshS -> OptixPrimeFunctionality -> Lightning::get_lightning ->
+ * converge_lightning); daisy_group gives such a host all GPUs of the box: one context per device (row block g of the matrix
+ * on device_ids[g], mesh and LBVH replicated), peer access enabled between all of them, peer pointers wired directly (no CUDA
+ * IPC, no NCCL, no second process).  device_ids == NULL: devices 0 .. ndev-1.
+ *   daisy_group_formfactors_build : every upper-triangle tile is traced by exactly one device and stored, with its mirror,
+ *                                   into the owners' matrices over NVLink; the devices build concurrently
+ *   daisy_group_solver_*          : the Lightning family over all devices; a pass is one asynchronous kernel launch per
+ *                                   device, the exchange of the residual happens inside the kernels (fused exchange)
+ * daisy_group_ctx(g, i) is device i's context for the per-context queries (row range, masks, digests, stats, closest hit). */
+typedef struct daisy_group daisy_group;
+typedef struct daisy_group_solver daisy_group_solver;
+int daisy_group_create(const float *vertices, int nv, const float *normals, int nn, const int32_t *tri_idx, int ntri,
+                       const int *device_ids, int ndev, daisy_group **out);
+void daisy_group_destroy(daisy_group *g);
+int daisy_group_size(daisy_group *g);
+daisy_ctx *daisy_group_ctx(daisy_group *g, int i);
+int daisy_group_set_samples(daisy_group *g, const float *uv, int S);
+int daisy_group_formfactors_build(daisy_group *g, int variant);
+int daisy_group_formfactors_read_rows(daisy_group *g, int row0, int nrows, float *out);
+int daisy_group_formfactors_write_rows(daisy_group *g, int row0, int nrows, const float *in);      /* the matrix-cache path, rows routed to their owners */
+int daisy_group_formfactors_to_csc(daisy_group *g, int64_t *nnz, float *values, int32_t *inner_idx, int32_t *outer_ptr);
+/* unique mutually facing pairs of the whole matrix, rays cast, slowest device's LBVH / form-factor kernel milliseconds */
+int daisy_group_formfactors_stats(daisy_group *g, int64_t *pairs, int64_t *rays, double *lbvh_ms, double *ff_ms);
+int daisy_group_solver_create(daisy_group *g, int K, const float *E, const float *M, int nmat, const int32_t *mat_idx,
+                              daisy_group_solver **out);
+void daisy_group_solver_destroy(daisy_group_solver *gs);
+int daisy_group_solver_reset(daisy_group_solver *gs);
+int daisy_group_solver_step(daisy_group_solver *gs, double *band_sums);       /* band_sums may be NULL: nothing waits */
+int daisy_group_solver_converge(daisy_group_solver *gs, double threshold, int per_band, int max_passes, int *passes_out);
+int daisy_group_solver_numpasses(daisy_group_solver *gs);
+int daisy_group_solver_band_sums(daisy_group_solver *gs, double *band_sums);
+int daisy_group_solver_read(daisy_group_solver *gs, float *B, float *residual);   /* K x N band-major, whole scene */
+int daisy_group_solver_write(daisy_group_solver *gs, const float *B, const float *residual);
 
 #ifdef __cplusplus
 }

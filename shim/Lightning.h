@@ -15,21 +15,21 @@ public:
     virtual glm::vec3 get_color_of_patch(int) = 0;
     virtual void converge_lightning() { // Lightning.h:145-151, :336-340, :410-415
         int passes = 0;
-        check(daisy_solver_converge(solver, threshold, per_band, 0, &passes));
+        check(daisy_group_solver_converge(solver, threshold, per_band, 0, &passes));
         numpasses = passes;
         fetch();
     }
     virtual void increment_lightpass() {
-        check(daisy_solver_step(solver, nullptr));
-        numpasses = daisy_solver_numpasses(solver);
+        check(daisy_group_solver_step(solver, nullptr));
+        numpasses = daisy_group_solver_numpasses(solver);
         fetch();
     }
     virtual void reset() {
-        check(daisy_solver_reset(solver));
+        check(daisy_group_solver_reset(solver));
         numpasses = 0;
         fetch();
     }
-    virtual ~Lightning() { daisy_solver_destroy(solver); }
+    virtual ~Lightning() { daisy_group_solver_destroy(solver); }
     int numpasses = 0;
     std::vector<std::vector<float>> lightningvalues, residualvector; // K x N, band-major (Lightning.h:107-109)
 
@@ -37,7 +37,7 @@ protected:
     bool cuda_on = false;
     SpMat RadMat;
     float emission_value = 0;
-    daisy_solver *solver = nullptr;
+    daisy_group_solver *solver = nullptr; // one solver per GPU of optixP's group behind one handle
     double threshold = 1e-4;
     int per_band = 1;
     int K = 0, N = 0;
@@ -92,7 +92,7 @@ protected:
             std::fill(rows.begin(), rows.begin() + (size_t)nr * n, 0.f);
             for (int r = 0; r < nr; r++)
                 for (Eigen::SparseMatrix<float, Eigen::RowMajor>::InnerIterator it(R, r0 + r); it; ++it) rows[(size_t)r * n + it.col()] = it.value();
-            if (!check(daisy_formfactors_write_rows(optixP.ctx, r0, nr, rows.data()))) return;
+            if (!check(daisy_group_formfactors_write_rows(optixP.group, r0, nr, rows.data()))) return;
         }
     }
     void initMatFromFile(MeshS &mesh, OptixPrimeFunctionality &optixP, char *matfile) { // Lightning.h:84-96
@@ -112,13 +112,13 @@ protected:
     }
     void create(MeshS &mesh, OptixPrimeFunctionality &optixP, int K_, const std::vector<float> &E, const std::vector<float> &M) {
         K = K_; N = mesh.numtriangles;
-        check(daisy_solver_create(optixP.ctx, K, E.data(), M.data(), (int)mesh.materials.size(), mesh.materialIndexPerTriangle.data(), &solver));
+        check(daisy_group_solver_create(optixP.group, K, E.data(), M.data(), (int)mesh.materials.size(), mesh.materialIndexPerTriangle.data(), &solver));
         lightningvalues.assign(K, std::vector<float>(N));
         residualvector.assign(K, std::vector<float>(N));
     }
     void fetch() {
         std::vector<float> B((size_t)K * N), R((size_t)K * N);
-        if (!check(daisy_solver_read(solver, B.data(), R.data()))) return;
+        if (!check(daisy_group_solver_read(solver, B.data(), R.data()))) return;
         for (int k = 0; k < K; k++) {
             std::copy(B.begin() + (size_t)k * N, B.begin() + (size_t)(k + 1) * N, lightningvalues[k].begin());
             std::copy(R.begin() + (size_t)k * N, R.begin() + (size_t)(k + 1) * N, residualvector[k].begin());

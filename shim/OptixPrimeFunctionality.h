@@ -2,8 +2,9 @@
 // (reference: visual studio/OptixPrimeFunctionality.h:24-48, .cpp:6-81, :133-271, :311-366), forwarding to the
 // C-ABI of include/daisy_b200.h.  Host code written against DaisyRiot keeps compiling: same class, same method
 // names and argument lists for optixQuery / cudaCalculateRadiosityMatrix / calculateRadiosityMatrix /
-// calculateVisibility / p2pFormfactor.  The OptiX Prime context/model members are gone (nothing here uses OptiX);
-// the camera/picking helpers traceScreen and intersectMouse are UI code outside this path (they only need optixQuery).
+// calculateVisibility / p2pFormfactor / traceScreen / intersectMouse.  The OptiX Prime context/model members are gone
+// (nothing here uses OptiX).  One extra constructor argument, `ndevices`, spreads the matrix and the solve over that many
+// GPUs of the box from this one process (daisy_group_*); the default 1 is the reference's single-device behaviour.
 //
 // Error behaviour follows the reference: failures are printed to std::cerr and execution continues
 // (.cpp:45-53, :72-79, parallellism.cuh:21-26); the C layer underneath is strict and keeps the message.
@@ -13,7 +14,9 @@
 #include <cstdlib>
 #include <iostream>
 #include <vector>
+#include <cmath>
 #include <glm/glm.hpp>
+#include <glm/gtc/matrix_transform.hpp>
 #include <Eigen/Sparse>
 #include "Vertex.h"   // reference headers, unchanged: vertex::TriangleIndex
 #include "Defines.h"  // UV, RAYS_PER_PATCH
@@ -23,8 +26,27 @@
 typedef Eigen::SparseMatrix<float> SpMat;
 typedef Eigen::Triplet<double> Tripl;
 
-namespace optix { struct float2 { float x, y; }; struct float3 { float x, y, z; }; }
-namespace optix_functionality { struct Hit { float t; int triangleId; optix::float2 uv; }; } // optix_functionality.h:10-14
+// the optix:: vector vocabulary the reference's host code uses (Camera.h, optix_functionality.h); the OptiX SDK headers are
+// no longer needed.  Skipped when the includer already has them (define DAISY_HAVE_OPTIX_MATH).
+#ifndef DAISY_HAVE_OPTIX_MATH
+namespace optix {
+struct float2 { float x, y; };
+struct float3 { float x, y, z; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float3 make_float3(float x, float y, float z) { float3 r; r.x = x; r.y = y; r.z = z; return r; }
+static inline float3 operator+(const float3 &a, const float3 &b) { return make_float3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline float3 operator-(const float3 &a, const float3 &b) { return make_float3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline float3 operator*(const float3 &a, float s) { return make_float3(a.x * s, a.y * s, a.z * s); }
+static inline float3 operator*(float s, const float3 &a) { return make_float3(a.x * s, a.y * s, a.z * s); }
+static inline float dot(const float3 &a, const float3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline float3 normalize(const float3 &v) { return v * (1.0f / sqrtf(dot(v, v))); }
+} // namespace optix
+#endif
+namespace optix_functionality {
+struct Hit { float t; int triangleId; optix::float2 uv; };                                  // optix_functionality.h:10-14
+static inline optix::float3 glm2optixf3(glm::vec3 v) { return optix::make_float3(v.x, v.y, v.z); } // optix_functionality.cpp
+static inline glm::vec3 optix2glmf3(optix::float3 v) { return glm::vec3(v.x, v.y, v.z); }
+} // namespace optix_functionality
 namespace parallellism { struct Tripl { int m_row, m_col; double m_value; }; }               // parallellism.cuh:30-33
 
 static_assert(sizeof(optix_functionality::Hit) == sizeof(daisy_hit), "Hit layout");
@@ -33,14 +55,20 @@ static_assert(sizeof(vertex::TriangleIndex) == 6 * sizeof(int), "TriangleIndex l
 
 class OptixPrimeFunctionality {
 public:
-    daisy_ctx *ctx = nullptr; // replaces optix::prime::Context contextP + optix::prime::Model model
+    daisy_group *group = nullptr; // replaces optix::prime::Context contextP + optix::prime::Model model: one context per GPU
+    daisy_ctx *ctx = nullptr;     // the first device's context (whole mesh + LBVH): closest-hit queries, per-pair entry points
 
     // .cpp:36-64: build the acceleration structure over the triangle soup and fix the 50-sample pattern.
-    // seed < 0 keeps the reference's behaviour (srand(time)); pass a seed to make runs repeatable.
-    explicit OptixPrimeFunctionality(MeshS &mesh, int device = 0, long seed = -1) {
-        report(daisy_ctx_create(reinterpret_cast<const float *>(mesh.vertices.data()), (int)mesh.vertices.size(),
-                                reinterpret_cast<const float *>(mesh.normals.data()), (int)mesh.normals.size(),
-                                reinterpret_cast<const int32_t *>(mesh.triangleIndices.data()), (int)mesh.triangleIndices.size(), device, &ctx));
+    // seed < 0 keeps the reference's behaviour (srand(time)); pass a seed to make runs repeatable.  ndevices > 1: devices
+    // device .. device + ndevices - 1 share the matrix (row blocks) and the solve.
+    explicit OptixPrimeFunctionality(MeshS &mesh, int device = 0, long seed = -1, int ndevices = 1) {
+        std::vector<int> ids;
+        for (int i = 0; i < (ndevices > 1 ? ndevices : 1); i++) ids.push_back(device + i);
+        if (report(daisy_group_create(reinterpret_cast<const float *>(mesh.vertices.data()), (int)mesh.vertices.size(),
+                                      reinterpret_cast<const float *>(mesh.normals.data()), (int)mesh.normals.size(),
+                                      reinterpret_cast<const int32_t *>(mesh.triangleIndices.data()), (int)mesh.triangleIndices.size(), ids.data(),
+                                      (int)ids.size(), &group)))
+            ctx = daisy_group_ctx(group, 0);
         rands.resize(RAYS_PER_PATCH);
         std::srand(seed < 0 ? (unsigned)std::time(nullptr) : (unsigned)seed);
         for (size_t i = 0; i < RAYS_PER_PATCH; i++) {
@@ -52,13 +80,13 @@ public:
         }
         setSamples(rands);
     }
-    ~OptixPrimeFunctionality() { daisy_ctx_destroy(ctx); }
+    ~OptixPrimeFunctionality() { daisy_group_destroy(group); } // destroy the Lightning objects first: their solvers live on these contexts
     OptixPrimeFunctionality(const OptixPrimeFunctionality &) = delete;
     OptixPrimeFunctionality &operator=(const OptixPrimeFunctionality &) = delete;
 
     void setSamples(const std::vector<UV> &r) {
         rands = r;
-        if (ctx) report(daisy_ctx_set_samples(ctx, reinterpret_cast<const float *>(rands.data()), (int)rands.size()));
+        if (group) report(daisy_group_set_samples(group, reinterpret_cast<const float *>(rands.data()), (int)rands.size()));
     }
 
     // .cpp:66-81 -- rays: origin,direction pairs; hits: one Hit per ray (miss: t < 0)
@@ -106,12 +134,12 @@ public:
     std::vector<Eigen::Triplet<double>> calculateAllVisibility(std::vector<parallellism::Tripl> & /*tripletlist*/, MeshS &mesh,
                                                                std::vector<UV> & /*rands*/) {
         std::vector<Eigen::Triplet<double>> out;
-        if (!report(daisy_formfactors_build(ctx, DAISY_FF_DEVICE))) return out;
+        if (!report(daisy_group_formfactors_build(group, DAISY_FF_DEVICE))) return out;
         int64_t nnz = 0;
-        if (!report(daisy_formfactors_to_csc(ctx, &nnz, nullptr, nullptr, nullptr))) return out;
+        if (!report(daisy_group_formfactors_to_csc(group, &nnz, nullptr, nullptr, nullptr))) return out;
         std::vector<float> val((size_t)nnz);
         std::vector<int> inner((size_t)nnz), outer((size_t)mesh.numtriangles + 1);
-        if (!report(daisy_formfactors_to_csc(ctx, &nnz, val.data(), inner.data(), outer.data()))) return out;
+        if (!report(daisy_group_formfactors_to_csc(group, &nnz, val.data(), inner.data(), outer.data()))) return out;
         out.reserve((size_t)nnz);
         for (int c = 0; c < mesh.numtriangles; c++)
             for (int i = outer[c]; i < outer[c + 1]; i++) out.emplace_back(inner[i], c, (double)val[i]);
@@ -156,7 +184,81 @@ public:
         return hit[0].triangleId == patches[1].triangleId;
     }
 
+    // .cpp:83-131 -- camera ray cast + shading.  RenderContext is the reference's Drawer::RenderContext (taken by value like
+    // there; its members are references) or any struct with the same members: camera, optixView, trianglesonScreen, mesh,
+    // lightning, radiosityRendering, antialiasing, supersampling.  Closest hit, isFacingBack, Drawer::interpolate
+    // (Drawer.cpp:161-186), the supersample average and the clamp run in one kernel; trianglesonScreen (the picking index)
+    // is rebuilt from the hit records in the reference's x-major pixel order.
+    template <class RenderContext>
+    void traceScreen(RenderContext cntxt) {
+        const int W = cntxt.camera.pixwidth, H = cntxt.camera.pixheight;
+        const int samples = cntxt.antialiasing ? cntxt.supersampling : 1;
+        cntxt.optixView.resize((size_t)W * H);
+        std::vector<optix::float3> rays;
+        cntxt.camera.gen_rays_for_screen(rays, cntxt.antialiasing);
+        const int N = (int)cntxt.mesh.triangleIndices.size();
+        std::vector<glm::vec3> rgb((size_t)N);
+        for (int i = 0; i < N; i++)
+            rgb[(size_t)i] = cntxt.radiosityRendering ? cntxt.lightning.get_color_of_patch(i) : cntxt.mesh.materials[cntxt.mesh.materialIndexPerTriangle[i]].rgbcolor;
+        std::vector<optix_functionality::Hit> hits((size_t)W * H * samples);
+        const glm::vec3 eye = optix_functionality::optix2glmf3(cntxt.camera.eye);
+        if (!report(daisy_trace_screen(ctx, W, H, samples, reinterpret_cast<const float *>(rays.data()), &eye.x, reinterpret_cast<const float *>(rgb.data()),
+                                       cntxt.radiosityRendering ? 1 : 0, reinterpret_cast<float *>(cntxt.optixView.data()),
+                                       reinterpret_cast<daisy_hit *>(hits.data()))))
+            return;
+        cntxt.trianglesonScreen.clear();
+        cntxt.trianglesonScreen.resize((size_t)N);
+        for (int x = 0; x < W; x++)
+            for (int y = 0; y < H; y++)
+                for (int i = 0; i < samples; i++) {
+                    const optix_functionality::Hit &h = hits[((size_t)y * W + x) * samples + i];
+                    if (h.t > 0 && !isFacingBack(eye, h.triangleId, cntxt.mesh)) {
+                        MatrixIndex index = {};
+                        index.col = x; index.row = y; index.uv = { h.uv.x, h.uv.y };
+                        cntxt.trianglesonScreen[(size_t)h.triangleId].push_back(index);
+                    }
+                }
+    }
+
+    // .cpp:471-517 -- picking: one ray through the cursor; the first pick selects patch 0, the second patch 1 and shoots a
+    // ray between them.  DebugLine / Camera are the reference's types (or look-alikes with left, debugtriangles / eye, dir,
+    // up, viewport).
+    template <class DebugLine, class CameraT>
+    bool intersectMouse(DebugLine &debugline, double xpos, double ypos, CameraT &camera, std::vector<std::vector<MatrixIndex>> & /*trianglesonScreen*/,
+                        std::vector<glm::vec3> & /*optixView*/, std::vector<optix_functionality::Hit> &patches, MeshS &mesh) {
+        bool hitB = true;
+        std::vector<optix::float3> ray(2);
+        std::vector<optix_functionality::Hit> hit(1);
+        glm::mat4x4 lookat = glm::lookAt(optix_functionality::optix2glmf3(camera.eye), optix_functionality::optix2glmf3(camera.dir), optix_functionality::optix2glmf3(camera.up));
+        glm::mat4x4 projection = glm::perspective(45.0f, (float)(800) / (float)(600), 0.1f, 1000.0f);
+        ray[0] = optix_functionality::glm2optixf3(glm::unProject(glm::vec3(xpos, ypos, 0.0), lookat, projection, camera.viewport));
+        ray[1] = optix_functionality::glm2optixf3(glm::unProject(glm::vec3(xpos, ypos, 1.0), lookat, projection, camera.viewport));
+        optixQuery(1, ray, hit);
+        if (hit[0].t > 0) {
+            printf("\nhit triangle: %i ", hit[0].triangleId);
+            if (debugline.left) patches[0] = hit[0];
+            else {
+                patches[1] = hit[0];
+                printf("\nshoot ray between patches \n");
+                printf("patch triangle 1: %i \n", patches[0].triangleId);
+                printf("patch triangle 2: %i \n", patches[1].triangleId);
+                hitB = shootPatchRay(patches, mesh);
+                printf("\ndid it hit? %i", hitB);
+            }
+            debugline.left = !debugline.left;
+            debugline.debugtriangles.push_back(hit[0].triangleId);
+        } else {
+            printf("miss!");
+            hitB = false;
+            patches.clear();
+            patches.resize(2);
+            debugline.left = true;
+        }
+        return hitB;
+    }
+
     std::vector<UV> rands;
+    bool refill_RadMat = true; // false: leave the caller's Eigen matrix empty after a build (large scenes: the matrix lives on the GPUs)
 
 private:
     static glm::vec3 centre(int tri, MeshS &mesh) { // triangle_math.cpp:16-21
@@ -181,17 +283,18 @@ private:
     void build(SpMat &RadMat, MeshS &mesh, int variant) {
         std::cout << "Calculating radiosity matrix..." << std::endl;
         std::cout << "Number of triangles: " << mesh.triangleIndices.size() << std::endl;
-        if (!report(daisy_formfactors_build(ctx, variant))) return;
-        int64_t pairs = 0, owned = 0, rays = 0; double lbvh = 0, ff = 0;
-        daisy_formfactors_stats(ctx, &pairs, &owned, &rays, &lbvh, &ff);
-        std::cout << "Calculation time of form factors + visibility: " << ff * 1e-3 << " s (" << rays << " rays)" << std::endl;
+        if (!report(daisy_group_formfactors_build(group, variant))) return;
+        int64_t pairs = 0, rays = 0; double lbvh = 0, ff = 0;
+        daisy_group_formfactors_stats(group, &pairs, &rays, &lbvh, &ff);
+        std::cout << "Calculation time of form factors + visibility: " << ff * 1e-3 << " s (" << rays << " rays, " << daisy_group_size(group) << " GPU(s))" << std::endl;
+        if (!refill_RadMat) { std::cout << "... done! (matrix resident on the GPUs, RadMat not refilled)" << std::endl; return; }
         int64_t nnz = 0;
-        if (!report(daisy_formfactors_to_csc(ctx, &nnz, nullptr, nullptr, nullptr))) return;
+        if (!report(daisy_group_formfactors_to_csc(group, &nnz, nullptr, nullptr, nullptr))) return;
         if (nnz > 0x7fffffffLL) { std::cerr << "RadMat not refilled: more non-zeros than Eigen's int index holds (matrix stays on the GPU)" << std::endl; return; }
         RadMat.resize(mesh.numtriangles, mesh.numtriangles);
         RadMat.makeCompressed();
         RadMat.resizeNonZeros((int)nnz);
-        report(daisy_formfactors_to_csc(ctx, &nnz, RadMat.valuePtr(), RadMat.innerIndexPtr(), RadMat.outerIndexPtr()));
+        report(daisy_group_formfactors_to_csc(group, &nnz, RadMat.valuePtr(), RadMat.innerIndexPtr(), RadMat.outerIndexPtr()));
         std::cout << "... done!" << std::endl;
     }
     static bool report(int rc) {

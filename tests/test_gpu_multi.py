@@ -118,3 +118,69 @@ def test_two_gpu_sharded_build_and_exchange(tmp_path, peer, fused):
     assert np.allclose(outs[0]["sums32"], np.array(sums32), rtol=2e-6) and np.array_equal(outs[0]["sums32"], outs[1]["sums32"])
     L.daisy_solver_destroy(s)
     p.close()
+
+
+
+def test_single_process_device_group_matches_single_gpu():
+    """daisy_group_*: two GPUs behind ONE host process (no torch.distributed, no CUDA IPC) -- matrix bit-identical to the
+    single-GPU build, gather / converge / reset / whole-scene read and write equal to the single-GPU solver (1e-5), same
+    pass count under the reference's stop rule."""
+    import ctypes as C
+    import daisyriot_b200 as dz
+    from conftest import assert_rel
+    from daisyriot_b200 import _lib, scenes
+    if dz.lib().daisy_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = scenes.cornell_box(2048)
+    uv = scenes.msvc_sample_pattern(1)
+    mesh = dz.MeshS.from_scene(sc)
+    p = dz.OptixPrimeFunctionality(mesh, rands=uv)
+    F1 = p.cudaCalculateRadiosityMatrix().rows()
+    grp = dz.DeviceGroup(mesh, devices=[0, 1], rands=uv)
+    F2 = grp.cudaCalculateRadiosityMatrix().rows()
+    assert np.array_equal(F2.view(np.uint32), F1.view(np.uint32))
+    assert grp.stats()["pairs"] == p.stats()["pairs_traced"]
+    assert grp.device(1).row_range == (1024, 2048)
+    K = 9
+    rng = np.random.RandomState(3)
+    M = rng.uniform(0, 0.3, (len(sc.materials), K, K)).astype(np.float32)
+    E = (rng.uniform(0, 7, (K, 2048)) * (rng.uniform(0, 1, (K, 2048)) < 0.1)).astype(np.float32)
+    L = _lib.lib()
+    s = C.c_void_p()
+    _lib.check(L.daisy_solver_create(p._ctx, K, _lib.fptr(E), _lib.fptr(M), M.shape[0], _lib.iptr(sc.mat_idx), C.byref(s)))
+    gs = dz.GroupSolver(grp, K, E, M, sc.mat_idx)
+    for it in range(3):
+        t = np.zeros(K)
+        _lib.check(L.daisy_solver_step(s, t.ctypes.data_as(C.POINTER(C.c_double))))
+        got = gs.step(True)
+        assert np.allclose(got, t, rtol=1e-6)
+    gs.step(False); gs.step(False)  # back-to-back passes, nothing waits on the host
+    for _ in range(2):
+        _lib.check(L.daisy_solver_step(s, None))
+    B1, R1 = np.empty_like(E), np.empty_like(E)
+    _lib.check(L.daisy_solver_read(s, _lib.fptr(B1), _lib.fptr(R1)))
+    B2, R2 = gs.read()
+    for k in range(K):
+        assert_rel(B2[k], B1[k], ("B", k)); assert_rel(R2[k], R1[k], ("residual", k))
+    assert gs.numpasses == 5
+    # the reference's stop rule through both
+    _lib.check(L.daisy_solver_reset(s))
+    gs.reset()
+    n1 = C.c_int()
+    _lib.check(L.daisy_solver_converge(s, 1e-3, 1, 500, C.byref(n1)))
+    n2 = gs.converge(1e-3, True, 500)
+    assert n2 == n1.value and n2 > 3
+    # whole-scene write: every device receives its own rows only, the residual slices travel over NVLink
+    gs.write(B1, R1)
+    _lib.check(L.daisy_solver_write(s, _lib.fptr(B1), _lib.fptr(R1)))
+    t = np.zeros(K)
+    _lib.check(L.daisy_solver_step(s, t.ctypes.data_as(C.POINTER(C.c_double))))
+    got = gs.step(True)
+    assert np.allclose(got, t, rtol=1e-6)
+    B1b, R1b = np.empty_like(E), np.empty_like(E)
+    _lib.check(L.daisy_solver_read(s, _lib.fptr(B1b), _lib.fptr(R1b)))
+    B2b, R2b = gs.read()
+    for k in range(K):
+        assert_rel(B2b[k], B1b[k], ("B after write", k)); assert_rel(R2b[k], R1b[k], ("residual after write", k))
+    L.daisy_solver_destroy(s)
+    gs.close(); grp.close(); p.close()
