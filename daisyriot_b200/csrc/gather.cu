@@ -48,6 +48,7 @@ struct daisy_solver {
     unsigned long long *h_abort = nullptr, *d_abort_host = nullptr; // host-mapped abort marker of the fused exchange
     unsigned long long timeout_ns = 30000000000ull;                  // how long a pass waits for a peer's block (DAISY_EXCHANGE_TIMEOUT_MS)
     int R = 8, nsplit = 1, grid = 148, colw = 0;
+    int sk_S = 0, sk_L = 0, sk_total = 0, sk_grid = 0, sk_maxp = 1; // stream-K decomposition of the fused TMA kernel (plan())
     bool use_tma = true;
     bool use_mma = false;               // K = 16 / 32: tcgen05 3xTF32 path (gather_mma.cuh)
     bool fused_epi = false;             // k_gather_tma does the epilogue (and the exchange wait) itself: one launch per pass
@@ -119,7 +120,16 @@ struct GatherParams {
     float *partial;         // nsplit x nloc x K
     int nsplit, colw;       // column range width per split (multiple of G_TC)
     int nrb;                // row blocks
+    // stream-K decomposition of k_gather_tma (fused epilogue): the (row block, 256-column step) pairs of the whole matrix form
+    // one sequence of sk_total steps, row block major; CTA c streams the contiguous range [c sk_L, (c+1) sk_L) -- every SM
+    // gets the same number of steps whatever the matrix shape, and a row block is shared by at most a few CTAs ("pieces")
+    int sk;                 // 1: stream-K pieces, 0: (row block, column split) items
+    int sk_S, sk_L, sk_total; // steps per row block, steps per CTA, steps in total
 };
+
+// one unit of work of k_gather_tma: steps [s0, s1) of row block rb; idx / np = this piece's ordinal among / number of the
+// pieces that make up the row block (their partial sums are added in idx order)
+struct Piece { int rb, s0, s1, idx, np; };
 
 // stage the K bands of columns [j0, j0+w) of the exchange buffer into tile[k][0..w)
 template <int K>
@@ -297,6 +307,34 @@ struct FusedEpi {
     unsigned long long timeout_ns;
 };
 
+
+// the i-th piece of CTA `cta` (cursor: running position, start at 0); false when the CTA has no more work
+template <int T_COLS>
+__device__ __forceinline__ bool next_piece(const GatherParams &P, int cta, int ncta, int &cursor, Piece &p) {
+    if (P.sk) {
+        const int g0 = cta * P.sk_L + cursor, g1 = min(P.sk_total, (cta + 1) * P.sk_L);
+        if (g0 >= g1) return false;
+        p.rb = g0 / P.sk_S;
+        p.s0 = g0 - p.rb * P.sk_S;
+        p.s1 = min(P.sk_S, p.s0 + (g1 - g0));
+        const int first = (p.rb * P.sk_S) / P.sk_L, lastc = ((p.rb + 1) * P.sk_S - 1) / P.sk_L;
+        p.idx = cta - first;
+        p.np = lastc - first + 1;
+        cursor += p.s1 - p.s0;
+        return true;
+    }
+    const int item = cta + cursor * ncta;
+    if (item >= P.nrb * P.nsplit) return false;
+    p.rb = item / P.nsplit;
+    p.idx = item - p.rb * P.nsplit;
+    p.np = P.nsplit;
+    const int c_begin = p.idx * P.colw, c_end = min(P.ncols, c_begin + P.colw);
+    p.s0 = c_begin / T_COLS;
+    p.s1 = p.s0 + (c_end - c_begin + T_COLS - 1) / T_COLS;
+    cursor++;
+    return true;
+}
+
 template <int K>
 __global__ void __launch_bounds__((TmaCfg<K>::NCW + 3) * 32, 1)
 k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ FusedEpi E) {
@@ -317,8 +355,9 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int nitems = P.nrb * P.nsplit;
     uint32_t it = 0; // global step counter: stage = it % NST, phase = (it / NST) & 1
+    int cursor = 0;
+    Piece pc;
     if (warp > NCW) {
         // ------------------------------- epilogue warps (64 threads) -------------------------------
         // They take over each finished item from the consumers (named barriers 2/3: "item done", 4/5: "buffer free"), so
@@ -327,19 +366,19 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
         const int et = tid - (NCW + 1) * 32, ewarp = et >> 5;
         auto esync = [&]() { asm volatile("bar.sync 1, 64;" ::: "memory"); };
         unsigned nitem_done = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x, nitem_done++) {
-            const int rb = item / P.nsplit;
+        for (; next_piece<T_COLS>(P, blockIdx.x, gridDim.x, cursor, pc); nitem_done++) {
+            const int rb = pc.rb;
             const int buf = (int)(nitem_done & 1u);
-            DZ_ASSERT(rb >= 0 && rb < P.nrb);
+            DZ_ASSERT(rb >= 0 && rb < P.nrb && pc.idx >= 0 && pc.idx < pc.np);
             asm volatile("bar.sync %0, %1;" ::"r"(2 + buf), "n"(NCW * 32 + 64) : "memory"); // the consumers have written this item's sums
             bool last = true;
-            if (P.nsplit > 1) {
+            if (pc.np > 1) {
                 if (et == 0) {
                     // release: the consumers' partial rows (ordered before this thread by the named barrier) become visible
                     // device-wide before the arrival is counted -- barrier + one fence + atomic, the usual semaphore pattern
                     __threadfence();
                     const unsigned old = atomicAdd(&E.rb_arrive[rb], 1u);
-                    const int l = (old == (unsigned)P.nsplit - 1u);
+                    const int l = (old == (unsigned)pc.np - 1u);
                     if (l) E.rb_arrive[rb] = 0u;
                     *s_flag = l;
                 }
@@ -359,13 +398,13 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                     for (int k = 0; k < K; k++) Bv[k] = E.B[(size_t)k * P.n + row]; // issued first: independent of everything below
                     DZ_ASSERT(E.mat[row] >= 0 && row < P.n);
                     const float *Mp = E.M + (size_t)E.mat[row] * K * K;
-                    if (P.nsplit == 1) {
+                    if (pc.np == 1) {
 #pragma unroll
                         for (int k = 0; k < K; k++) b[k] = s_out[buf * (T_ROWS * K) + et * K + k];
                     } else {
 #pragma unroll
                         for (int k = 0; k < K; k++) b[k] = 0.0f;
-                        for (int sp = 0; sp < P.nsplit; sp++) { // fixed order: the result does not depend on which CTA came last
+                        for (int sp = 0; sp < pc.np; sp++) { // fixed order: the result does not depend on which CTA came last
                             const float *src = P.partial + ((size_t)sp * P.nloc + row) * K;
 #pragma unroll
                             for (int k = 0; k < K; k++) b[k] += __ldcg(src + k);
@@ -450,16 +489,12 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
         // single block's tail beyond n is zero-filled by the TMA unit)
         if (lane == 0) {
             unsigned ready = (E.enabled && E.wait_seq != 0ull) ? 0u : 0xffffffffu; // ranks whose block of the previous pass is known to be here
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const int rb = item / P.nsplit, split = item - rb * P.nsplit;
-                const int c_begin = split * P.colw;
-                const int c_end = min(P.ncols, c_begin + P.colw);
-                const int nstep = (c_end - c_begin + T_COLS - 1) / T_COLS;
-                const int row0 = rb * T_ROWS;
-                for (int s = 0; s < nstep; s++, it++) {
+            while (next_piece<T_COLS>(P, blockIdx.x, gridDim.x, cursor, pc)) {
+                const int row0 = pc.rb * T_ROWS;
+                for (int s = pc.s0; s < pc.s1; s++, it++) {
                     const int st = it % NST;
                     mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
-                    const int col0 = c_begin + s * T_COLS;
+                    const int col0 = s * T_COLS;
                     float *sf = stages + (size_t)st * STAGE_F;
                     mbar_expect_tx(&full[st], (uint32_t)tma_stage_bytes<K>());
                     tma_load_2d(sf, &tmF, col0, row0, &full[st]);
@@ -490,18 +525,15 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     } else {
         // ------------------------------- consumers ------------------------------
         unsigned nitem_done = 0;
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const int rb = item / P.nsplit, split = item - rb * P.nsplit;
-            const int c_begin = split * P.colw;
-            const int c_end = min(P.ncols, c_begin + P.colw);
-            const int nstep = (c_end - c_begin + T_COLS - 1) / T_COLS;
-            const int row_base = rb * T_ROWS + warp * RW;
+        while (next_piece<T_COLS>(P, blockIdx.x, gridDim.x, cursor, pc)) {
+            const int split = pc.idx;
+            const int row_base = pc.rb * T_ROWS + warp * RW;
             float acc[RW][K];
 #pragma unroll
             for (int r = 0; r < RW; r++)
 #pragma unroll
                 for (int k = 0; k < K; k++) acc[r][k] = 0.0f;
-            for (int s = 0; s < nstep; s++, it++) {
+            for (int s = pc.s0; s < pc.s1; s++, it++) {
                 const int st = it % NST;
                 mbar_wait(&full[st], (it / NST) & 1);
 #pragma unroll
@@ -544,7 +576,7 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
 #pragma unroll
                 for (int r = 0; r < RW; r++) {
                     int row = row_base + r;
-                    if (E.enabled && P.nsplit == 1) {
+                    if (E.enabled && pc.np == 1) {
                         float *dst = s_out + buf * (T_ROWS * K) + (warp * RW + r) * K;
 #pragma unroll
                         for (int k = 0; k < K; k++) dst[k] = acc[r][k];
@@ -705,6 +737,7 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
     P.F = c->d_F; P.ldF = c->ldF; P.nloc = s->nloc; P.ncols = s->G * s->n; P.n = s->n;
     P.res = s->d_res[s->cur]; P.bstride = s->bstride; P.partial = s->d_partial;
     P.nsplit = s->nsplit; P.colw = s->colw; P.nrb = (s->nloc + G_WARPS * s->R - 1) / (G_WARPS * s->R);
+    P.sk = 0; P.sk_S = P.sk_L = P.sk_total = 0;
     int rc;
     if (s->use_mma && (K == 16 || K == 32)) {
         if constexpr (K == 16 || K == 32) {
@@ -730,6 +763,8 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
             attr_done = true;
         }
         P.nrb = (s->nloc + tma_rows<K>() - 1) / tma_rows<K>();
+        P.sk = s->fused_epi ? 1 : 0; P.sk_S = s->sk_S; P.sk_L = s->sk_L; P.sk_total = s->sk_total;
+        const int grid = s->fused_epi ? s->sk_grid : s->grid;
         FusedEpi F;
         memset(&F, 0, sizeof(F));
         F.enabled = s->fused_epi ? 1 : 0;
@@ -750,7 +785,7 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
                 }
             }
         }
-        k_gather_tma<K><<<s->grid, (TmaCfg<K>::NCW + 3) * 32, smem, c->stream>>>(P, s->tmF, s->tmRes[s->cur], F);
+        k_gather_tma<K><<<grid, (TmaCfg<K>::NCW + 3) * 32, smem, c->stream>>>(P, s->tmF, s->tmRes[s->cur], F);
         DZ_CUDA(cudaGetLastError());
         if (s->fused_epi) return DAISY_OK; // the whole pass was that one launch
         rc = DAISY_OK;
@@ -894,6 +929,17 @@ static void plan(daisy_solver *s) {
     int colw = (ncols + s->nsplit - 1) / s->nsplit;
     s->colw = ((colw + G_TC - 1) / G_TC) * G_TC; // multiple of 512 columns (and of the 128-column TMA step)
     s->nsplit = (ncols + s->colw - 1) / s->colw;
+    if (s->fused_epi) {
+        // stream-K: the (row block, column step) sequence cut into one contiguous, equally long range per SM
+        const int trows = (s->Kp == 32) ? 32 : 64, tcols = (s->Kp <= 9) ? 256 : 128; // = tma_rows<Kp>() x TmaCfg<Kp>::COLS
+        const int nrb = (s->nloc + trows - 1) / trows;
+        s->sk_S = (ncols + tcols - 1) / tcols;
+        s->sk_total = nrb * s->sk_S;
+        s->sk_grid = s->sk_total < sms ? (s->sk_total > 0 ? s->sk_total : 1) : sms;
+        s->sk_L = (s->sk_total + s->sk_grid - 1) / s->sk_grid;
+        if (s->sk_L < 1) s->sk_L = 1;
+        s->sk_maxp = s->sk_S / s->sk_L + 2;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -966,7 +1012,7 @@ extern "C" int daisy_solver_create(daisy_ctx *ctx, int K, const float *E, const 
     SC(cudaMalloc(&s->d_B, sizeof(float) * (size_t)s->Kp * s->n));
     SC(cudaMalloc(&s->d_M, sizeof(float) * (size_t)nmat * s->Kp * s->Kp));
     SC(cudaMalloc(&s->d_mat, sizeof(int) * (size_t)(s->nloc > 0 ? s->nloc : 1)));
-    SC(cudaMalloc(&s->d_partial, sizeof(float) * (size_t)s->nsplit * (s->nloc > 0 ? s->nloc : 1) * s->Kp));
+    SC(cudaMalloc(&s->d_partial, sizeof(float) * (size_t)(s->nsplit > s->sk_maxp ? s->nsplit : s->sk_maxp) * (s->nloc > 0 ? s->nloc : 1) * s->Kp));
     SC(cudaMalloc(&s->d_cta_sums, sizeof(double) * 148 * s->Kp));
     SC(cudaMalloc(&s->d_done, sizeof(unsigned int)));
     SC(cudaMemset(s->d_done, 0, sizeof(unsigned int)));
