@@ -714,10 +714,10 @@ __global__ void k_wait_flags(unsigned long long *flags, int G, unsigned long lon
 template <int K, int R>
 static int launch_partial(daisy_solver *s, const GatherParams &P) {
     size_t smem = 2 * K * G_TC * sizeof(float) + 64;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = { false }; // per device: a function attribute belongs to the device's context
+    if (!attr_done[s->ctx->device & 63]) {
         DZ_CUDA(cudaFuncSetAttribute(k_gather_partial<K, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        attr_done[s->ctx->device & 63] = true;
     }
     k_gather_partial<K, R><<<s->grid, G_THREADS, smem, s->ctx->stream>>>(P);
     DZ_CUDA(cudaGetLastError());
@@ -742,10 +742,10 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
     if (s->use_mma && (K == 16 || K == 32)) {
         if constexpr (K == 16 || K == 32) {
             constexpr size_t smem = mm_smem_bytes<K>();
-            static bool attr_done = false;
-            if (!attr_done) {
+            static bool attr_done[64] = { false }; // per device
+            if (!attr_done[c->device & 63]) {
                 DZ_CUDA(cudaFuncSetAttribute(k_gather_mma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_done = true;
+                attr_done[c->device & 63] = true;
             }
             k_split_residual<K><<<(s->ncolsP + 255) / 256, 256, 0, c->stream>>>(s->d_res[s->cur], s->bstride, s->n, s->G * s->n, s->ncolsP, s->d_split);
             DZ_CUDA(cudaGetLastError());
@@ -757,10 +757,10 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
     } else if (s->use_tma) {
         constexpr int NST = tma_nstage<K>();
         size_t smem = (size_t)NST * tma_stage_bytes<K>() + 2 * NST * sizeof(uint64_t) + tma_epi_bytes<K>();
-        static bool attr_done = false;
-        if (!attr_done) {
+        static bool attr_done[64] = { false }; // per device
+        if (!attr_done[c->device & 63]) {
             DZ_CUDA(cudaFuncSetAttribute(k_gather_tma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
+            attr_done[c->device & 63] = true;
         }
         P.nrb = (s->nloc + tma_rows<K>() - 1) / tma_rows<K>();
         P.sk = s->fused_epi ? 1 : 0; P.sk_S = s->sk_S; P.sk_L = s->sk_L; P.sk_total = s->sk_total;
