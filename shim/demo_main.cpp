@@ -2,6 +2,7 @@
 // reference's own MeshS/Material code, build form factors and converge the lighting through the shim classes.
 //   shim_demo <scene.obj> <mtl_dir/> <method 0|1|2> <emission_value> <seed> [rands.bin] [matrix cache file]   (cwd must hold color_tables/srgb.coeff)
 // Prints one line of results the parity test compares with the Python path.
+#include <chrono>
 #include <cstdio>
 #include <vector>
 #define TINYOBJLOADER_IMPLEMENTATION
@@ -91,10 +92,17 @@ int main(int argc, char **argv) {
     }
     float emission = (float)atof(argv[4]);
     int method = atoi(argv[3]);
+    // large scenes: the matrix has more non-zeros than an Eigen int index holds and lives on the GPUs only
+    if (getenv("DAISY_DEMO_NO_REFILL")) optixP.refill_RadMat = false;
+    const auto t0 = std::chrono::high_resolution_clock::now();
     Lightning *l = Lightning::get_lightning(method, mesh, optixP, emission, wavelengths, true, argc > 7 ? argv[7] : nullptr); // main.cpp:108 passes matfile
+    const double solve_s = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     double sum = 0;
     for (auto &band : l->lightningvalues) for (float v : band) sum += v;
     glm::vec3 c = l->get_color_of_patch(mesh.numtriangles / 2);
+    printf("SOLVE patches=%d gpus=%d passes=%d sumB=%.9e seconds=%.3f (form factors + converge_lightning, Lightning::get_lightning)\n", mesh.numtriangles, ndev,
+           l->numpasses, sum, solve_s);
+    if (getenv("DAISY_DEMO_SOLVE_ONLY")) { delete l; return 0; }
     // the batched visibility entry point on its own (OptixPrimeFunctionality.cpp:169-242): count and sum of the triplets
     std::vector<parallellism::Tripl> unoccluded;
     std::vector<Eigen::Triplet<double>> tr = optixP.calculateAllVisibility(unoccluded, mesh, optixP.rands);
