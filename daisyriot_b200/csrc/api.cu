@@ -31,6 +31,7 @@ static void free_ctx(daisy_ctx *c) {
         for (int g = 0; g < c->nranks && g < 16; g++)
             if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
     cudaFree(c->d_vertices); cudaFree(c->d_normals); cudaFree(c->d_tri); cudaFree(c->d_triverts); cudaFree(c->d_tribox); cudaFree(c->d_geom); cudaFree(c->d_plane); cudaFree(c->d_pid); cudaFree(c->d_nbr);
+    dz_free_faces(c);
     cudaFree(c->d_nodes); cudaFree(c->d_F); cudaFree(c->d_order); free(c->h_order); cudaFree(c->d_vadj_off); cudaFree(c->d_vadj);
     delete c;
 }
@@ -89,6 +90,16 @@ bool fit_plane(const std::vector<V3d> &pts, V3d &n, V3d &c) {
     return true;
 }
 } // namespace
+
+// plain-array form for faces.cu
+bool dz_fit_plane(const double *pts_xyz, size_t npts, double n_out[3], double c_out[3]) {
+    std::vector<V3d> pts(npts);
+    for (size_t i = 0; i < npts; i++) pts[i] = { pts_xyz[3 * i], pts_xyz[3 * i + 1], pts_xyz[3 * i + 2] };
+    V3d n, c;
+    if (!fit_plane(pts, n, c)) return false;
+    n_out[0] = n.x; n_out[1] = n.y; n_out[2] = n.z; c_out[0] = c.x; c_out[1] = c.y; c_out[2] = c.z;
+    return true;
+}
 
 static void assign_plane_ids(const float *vertices, const int32_t *tri_idx, int ntri, float ext, std::vector<int> &pid) {
     pid.assign((size_t)(ntri > 0 ? ntri : 1), 0);
@@ -265,6 +276,7 @@ extern "C" int daisy_ctx_create(const float *vertices, int nv, const float *norm
     {
         std::vector<int> pid;
         assign_plane_ids(vertices, tri_idx, ntri, ext, pid);
+        { const int rc_ = dz_build_faces(c, vertices, tri_idx, ntri, pid); if (rc_) { free_ctx(c); return rc_; } } // renumbers pid: face f = id f + 1
         CC(cudaMalloc(&c->d_pid, sizeof(int) * pid.size()));
         CC(cudaMemcpy(c->d_pid, pid.data(), sizeof(int) * pid.size(), cudaMemcpyHostToDevice));
     }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 #include <nvtx3/nvToolsExt.h>
 #include "../../include/daisy_b200.h"
 
@@ -226,6 +227,15 @@ struct __align__(16) TriVerts { float4 a, b, c; };
 // per-patch record for the 4x4 rule (80 B): 4 sub-centroids with sub-areas in w, then normal with area in w
 struct __align__(16) PatchGeom { float4 s[4]; float4 n; };
 
+// planar face grid (faces.cu): plane n.X = d, cell coordinates a = dot(X, ex.xyz) + ex.w, b = dot(X, ey.xyz) + ey.w
+#define DAISY_MAX_FACES 64
+struct __align__(16) DzFace {
+    float4 pl; // unit normal, d
+    float4 ex; // in-plane axis / cell size, offset
+    float4 ey;
+    int4 g;    // nx, ny, index of the face's first cell in the cell table, number of triangles
+};
+
 __device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -252,6 +262,12 @@ struct daisy_ctx {
     int *d_nbr = nullptr;       // per triangle: its neighbours in that plane, 32 ints ([0] = count), formfactor.cu k_tri_planes
     float4 *d_plane = nullptr;  // per triangle: unit geometric normal, w = smallest altitude if coplanar skipping is safe for it, else -1
     float ext = 0.f;            // largest scene extent
+    // planar face grids (faces.cu): face f = plane id f + 1
+    DzFace *d_faces = nullptr;
+    int *d_face_cells = nullptr; // per cell: -1 empty, else (offset into d_face_lists << 1) | covered
+    int *d_face_lists = nullptr; // per non-empty cell: count, triangle ids
+    int nfaces = 0;
+    int64_t face_cells = 0, face_list_ints = 0;
     // LBVH
     BvhNode *d_nodes = nullptr;
     int root = 0;
@@ -272,6 +288,8 @@ struct daisy_ctx {
 int dz_build_lbvh(daisy_ctx *ctx);                                   // bvh.cu
 int dz_launch_closest(daisy_ctx *ctx, int n, const float *d_rays, daisy_hit *d_hits); // bvh.cu
 int dz_precompute_geom(daisy_ctx *ctx);                              // formfactor.cu
+int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid); // faces.cu
+void dz_free_faces(daisy_ctx *c);                                    // faces.cu
 int dz_set_samples_const(daisy_ctx *ctx);                            // formfactor.cu
 int dz_unoccluded_rows(daisy_ctx *ctx, int variant, int row0, int nrows, daisy_tripl *d_out); // formfactor.cu
 struct daisy_solver;

@@ -402,20 +402,46 @@ __device__ __forceinline__ bool shaft_box(const Shaft &s, float lox, float loy, 
 // direct neighbours, which the edge samples test from the precomputed neighbour lists -- and, since every LBVH node
 // carries the plane id common to all triangles below it, whole subtrees of a wall the pair starts or ends on are never
 // entered.  Returns the number of candidates, or -1 if they do not fit SHAFT_CAP.
+//
+// Face grids (faces.cu): a child whose triangles all lie in face f (plane id f + 1 <= nfaces) is not entered either when every
+// ray of the pair meets that plane at |cos| >= FACE_COS_MIN -- the face goes into the pair's face mask instead and the rays
+// look their crossing up in the face's grid (pair_mask_warp).  The bound is the one of pair_premise: the ray directions are
+// convex combinations of the three vertex-to-vertex vectors D_i, so n.D_i of one sign gives cos >= min|n.D_i| / max|D_i|.
+#define FACE_COS_MIN 0.05f
 __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, int root, const Shaft &sh, int skip_lo, int skip_hi, int lo, int hi,
-                                                int *__restrict__ cand) {
+                                                int *__restrict__ cand, const TriVerts &A, const TriVerts &B, const DzFace *__restrict__ faces, int nfaces,
+                                                unsigned long long &fmask) {
     int n_main = 0;
     int stack[64];
     int sp = 0;
     int cur = root;
     bool overflow = false;
+    unsigned long long ftested = 0;
+    fmask = 0;
     if (cur < 0) return 0; // single-triangle hierarchy: no third triangle exists
+    auto face_ok = [&](int p) -> bool {
+        const unsigned long long bit = 1ull << (p - 1);
+        if (ftested & bit) return (fmask & bit) != 0;
+        ftested |= bit;
+        const float4 pl = __ldg(&faces[p - 1].pl);
+        const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
+        const float d1x = B.b.x - A.b.x, d1y = B.b.y - A.b.y, d1z = B.b.z - A.b.z;
+        const float d2x = B.c.x - A.c.x, d2y = B.c.y - A.c.y, d2z = B.c.z - A.c.z;
+        const float dm2 = fmaxf(d0x * d0x + d0y * d0y + d0z * d0z, fmaxf(d1x * d1x + d1y * d1y + d1z * d1z, d2x * d2x + d2y * d2y + d2z * d2z));
+        const float l0 = pl.x * d0x + pl.y * d0y + pl.z * d0z, l1 = pl.x * d1x + pl.y * d1y + pl.z * d1z, l2 = pl.x * d2x + pl.y * d2y + pl.z * d2z;
+        const float lmin = fminf(fabsf(l0), fminf(fabsf(l1), fabsf(l2)));
+        const bool ok = (l0 > 0.f) == (l1 > 0.f) && (l1 > 0.f) == (l2 > 0.f) && lmin * lmin >= (FACE_COS_MIN * FACE_COS_MIN) * dm2 && dm2 > 0.f;
+        if (ok) fmask |= bit;
+        return ok;
+    };
     while (!overflow) {
         const BvhNode nd = nodes[cur];
         const bool sl = nd.d.z != 0 && (nd.d.z == skip_lo || nd.d.z == skip_hi);
         const bool sr = nd.d.w != 0 && (nd.d.w == skip_lo || nd.d.w == skip_hi);
         bool hl = !sl && shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
         bool hr = !sr && shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
+        if (hl && nd.d.z > 0 && nd.d.z <= nfaces && face_ok(nd.d.z)) hl = false;
+        if (hr && nd.d.w > 0 && nd.d.w <= nfaces && face_ok(nd.d.w)) hr = false;
         if (hl && nd.d.x < 0) {
             const int k = ~nd.d.x;
             if (k != lo && k != hi) { DZ_ASSERT(k >= 0 && n_main <= SHAFT_CAP); if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
@@ -466,10 +492,15 @@ __device__ __forceinline__ void pair_premise(const TriVerts &A, const TriVerts &
 // watertight test.  Same predicate as ray_sees: sample i sees hi iff hi is accepted at t_hi and no other triangle k
 // is accepted with (t_k, k) < (t_hi, hi); lo takes part like any other triangle.  The main list is tested by every
 // sample, the ring list (coplanar with lo or hi, see shaft_candidates) only by the edge samples.
+struct FaceTables {
+    const DzFace *faces;
+    const int *cells, *lists;
+    float tm; // margin on the ray parameter: crossings within tm of either end point are resolved by explicit tests
+};
 __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox,
-                                                   const TriVerts &Tlo, const TriVerts &Thi, int hi, const int *cand,
-                                                   int n_main, const int *nbr_lo, const int *nbr_hi, int n_inner, float m_req, const float *s_uv,
-                                                   const unsigned char *s_perm, int S, int lane, int *wk, float4 *wb) {
+                                                   const TriVerts &Tlo, const TriVerts &Thi, int lo, int hi, const int *cand,
+                                                   int n_main, unsigned long long fmask, const FaceTables &ft, const int *nbr_lo, const int *nbr_hi, int n_inner,
+                                                   float m_req, const float *s_uv, const unsigned char *s_perm, int S, int lane, int *wk, float4 *wb) {
     unsigned mask_lo = 0, mask_hi = 0;
     for (int pass = 0; pass * 32 < S; pass++) {
         const int i = pass * 32 + lane;
@@ -484,6 +515,52 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         float thi = 0.f, uu, vv, tk;
         bool alive = (i < S) && wray_tri_sel(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv);
         if (alive && wray_tri_sel(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) alive = false;
+        // Face grids first: one plane crossing and one cell lookup per (ray, face).  A covered cell crossed safely between the
+        // ray's end points blocks the ray (some triangle of the face accepts it, faces.cu); an empty cell or a crossing beyond
+        // the end points cannot; everything else runs the watertight test on the cell's own short list.
+        if (fmask) {
+            unsigned long long fm = fmask;
+            bool any = __any_sync(0xffffffffu, alive);
+            while (fm && any) {
+                const int f = __ffsll((long long)fm) - 1;
+                fm &= fm - 1;
+                const float4 pl = __ldg(&ft.faces[f].pl);
+                const float ndir = pl.x * dir.x + pl.y * dir.y + pl.z * dir.z;
+                const float norg = pl.x * o.x + pl.y * o.y + pl.z * o.z;
+                const float t = __fdividef(pl.w - norg, ndir);
+                if (alive && t > -ft.tm && t < thi + ft.tm) {
+                    const float4 ex = __ldg(&ft.faces[f].ex), ey = __ldg(&ft.faces[f].ey);
+                    const int4 g = __ldg(&ft.faces[f].g);
+                    const float X = fmaf(t, dir.x, o.x), Y = fmaf(t, dir.y, o.y), Z = fmaf(t, dir.z, o.z);
+                    const float ca = fmaf(X, ex.x, fmaf(Y, ex.y, fmaf(Z, ex.z, ex.w)));
+                    const float cb = fmaf(X, ey.x, fmaf(Y, ey.y, fmaf(Z, ey.z, ey.w)));
+                    if (ca >= 0.f && cb >= 0.f && ca < (float)g.x && cb < (float)g.y) {
+                        const int c = __ldg(ft.cells + g.z + (int)cb * g.x + (int)ca);
+#ifdef DAISY_FF_STATS
+                        atomicAdd(&g_ffstats[15], 1ull);
+#endif
+                        if (c >= 0) {
+                            if ((c & 1) && t > ft.tm && t < thi - ft.tm) alive = false;
+                            else {
+                                const int *L = ft.lists + (c >> 1);
+                                const int n = __ldg(L);
+                                DZ_ASSERT(n > 0);
+                                for (int q = 1; q <= n; q++) {
+                                    const int k = __ldg(L + q);
+                                    if (k == lo || k == hi) continue;
+#ifdef DAISY_FF_STATS
+                                    atomicAdd(&g_ffstats[14], 1ull);
+#endif
+                                    const TriVerts tr = tv[k];
+                                    if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) { alive = false; break; }
+                                }
+                            }
+                        }
+                    }
+                }
+                any = __any_sync(0xffffffffu, alive);
+            }
+        }
         // reciprocal direction, kept finite: with inv = inf the pre-multiplied form would turn a box that straddles 0 on an
         // axis the ray is parallel to into (-inf, NaN) and reject it
         f3 inv = mk3(1.0f / (fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x)), 1.0f / (fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y)),
@@ -620,6 +697,10 @@ struct FFParams {
     const float4 *plane;  // per-triangle plane record (k_tri_planes)
     const int *pid;       // per-triangle plane id (0 = none)
     const int *nbr;       // per-triangle neighbour list in its own plane: NBR_CAP ints, [0] = count (k_tri_planes)
+    const DzFace *faces;  // planar face grids (faces.cu): face f = plane id f + 1
+    const int *face_cells, *face_lists;
+    int nfaces;
+    float face_tm;
     const int *order;     // tile composition: slot -> triangle id (-1 = empty slot); tile T holds slots [64 T, 64 T + 64)
     int n_inner;          // samples [0, n_inner) of the device-order pattern are inner samples
     int ring_on;          // coplanar skipping enabled
@@ -804,6 +885,8 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 if (c >= P.mrow0 && c < P.mrow1) P.masks[(size_t)(c - P.mrow0) * P.N + r] = mask;
             }
         };
+        FaceTables ftab;
+        ftab.faces = P.faces; ftab.cells = P.face_cells; ftab.lists = P.face_lists; ftab.tm = P.face_tm;
         while (true) { // 2a
             int q0 = 0;
             if (lane == 0) q0 = atomicAdd(&s_next, 32);
@@ -813,6 +896,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
             const int q = q0 + lane;
             int idx = 0, ncand = -2;
             float m_req = 0.f;
+            unsigned long long fmask = 0;
             if (q < nlist) {
                 idx = s_list[q];
                 const int rl = (idx >> 6) & 63, cl = idx & 63;
@@ -828,7 +912,8 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
                 bool on_lo = false, on_hi = false;
                 if (P.ring_on) pair_premise(A, B, sm.pl[ilo], sm.pl[ihi], on_lo, on_hi, m_req);
-                ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand);
+                ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand, A, B,
+                                         P.faces, P.nfaces, fmask);
                 if (ncand >= 0) ncand |= (on_lo ? 0x10000 : 0) | (on_hi ? 0x20000 : 0);
                 if (ncand < 0) { // the lists do not fit: flag the pair, phase 2b walks the LBVH per ray
                     s_list[q] = (unsigned short)(idx | PAIR_HEAVY);
@@ -843,10 +928,12 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 if (nc < 0) continue;
                 const int idj = __shfl_sync(0xffffffffu, idx, j);
                 const float mrq = __shfl_sync(0xffffffffu, m_req, j);
+                const unsigned long long fmj = (unsigned long long)__shfl_sync(0xffffffffu, (unsigned)fmask, j) |
+                                               ((unsigned long long)__shfl_sync(0xffffffffu, (unsigned)(fmask >> 32), j) << 32);
                 const int rl = (idj >> 6) & 63, cl = idj & 63;
                 const int ilo = (idj & PAIR_SWAP) ? TILE + cl : rl, ihi = (idj & PAIR_SWAP) ? rl : TILE + cl;
                 const TriVerts Tlo = s_tv[ilo], Thi = s_tv[ihi];
-                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, sm.id[ihi], warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff,
+                uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, sm.id[ilo], sm.id[ihi], warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, fmj, ftab,
                                                (nc & 0x10000) ? P.nbr + (size_t)sm.id[ilo] * NBR_CAP : nullptr,
                                                (nc & 0x20000) ? P.nbr + (size_t)sm.id[ihi] * NBR_CAP : nullptr, P.n_inner, mrq,
                                                sm.uv, sm.perm, P.S, lane, sm.u.p2.wk[tid >> 5], sm.u.p2.wb[tid >> 5]);
@@ -857,6 +944,8 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                     const int cat = nm == 0 ? 0 : (pc == 0 ? 1 : (pc == P.S ? 2 : 3)); // simple / occluded / visible / partial
                     atomicAdd(&g_ffstats[cat], 1ull); atomicAdd(&g_ffstats[4 + cat], (unsigned long long)nm); atomicAdd(&g_ffstats[8 + cat], (unsigned long long)((nc >> 16) & 3));
                     if (nm == 0 && pc == P.S) atomicAdd(&g_ffstats[12], 1ull);
+                    atomicAdd(&g_ffstats[13], (unsigned long long)__popcll(fmj));
+                    if (nm == 0 && fmj == 0) atomicAdd(&g_ffstats[18], 1ull);
                 }
                 {
                     const int nm = nc & 0xffff;
@@ -989,6 +1078,8 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     P.geom = ctx->d_geom; P.tv = ctx->d_triverts; P.tribox = ctx->d_tribox; P.scratch = nullptr; P.nodes = ctx->d_nodes; P.root = ctx->root; P.N = N; P.S = ctx->S;
     P.order = ctx->d_order;
     P.plane = ctx->d_plane; P.pid = ctx->d_pid; P.nbr = ctx->d_nbr; P.n_inner = ctx->n_nonedge;
+    P.faces = ctx->d_faces; P.face_cells = ctx->d_face_cells; P.face_lists = ctx->d_face_lists; P.nfaces = ctx->nfaces; P.face_tm = 4.0f * ctx->pad;
+    { const char *e = getenv("DAISY_FF_FACES"); if (e && e[0] == '0') P.nfaces = 0; }
     { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
@@ -1031,6 +1122,8 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
         for (int c = 0; c < 4; c++)
             fprintf(stderr, "ffstats %-18s pairs %12llu  mean n_main %7.1f  mean n_ring %6.1f\n", nm[c], h[c], h[c] ? (double)h[4 + c] / h[c] : 0.0, h[c] ? (double)h[8 + c] / h[c] : 0.0);
         fprintf(stderr, "ffstats simple&fully-visible %llu ; slab iterations pass0 %llu pass1 %llu\n", h[12], h[16], h[17]);
+        fprintf(stderr, "ffstats faces: %d grids, face entries over all pairs %llu, pairs with neither list nor face %llu, cell lookups %llu, explicit tests in cells %llu\n",
+                ctx->nfaces, h[13], h[18], h[15], h[14]);
         fprintf(stderr, "ffstats flush: rounds executed %llu, rounds if balanced over lanes %llu, tests queued %llu (%.1f lanes per executed round)\n",
                 h[22], h[20], h[21], h[22] ? (double)h[21] / h[22] : 0.0);
         {

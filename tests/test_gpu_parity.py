@@ -348,6 +348,22 @@ def test_coplanar_skipping_changes_nothing(dz, uv50, monkeypatch):
     assert np.array_equal(got["1"][1], got["0"][1])
 
 
+def test_face_grids_change_nothing(dz, uv50, monkeypatch):
+    """The planar face grids (faces.cu; formfactor.cu: shaft_candidates / pair_mask_warp) are a pure optimisation: with them
+    switched off (DAISY_FF_FACES=0) the triangles of a face are ordinary candidates again.  Matrix and masks must be
+    identical bit for bit."""
+    from daisyriot_b200 import scenes
+    sc = scenes.cornell_box(8192)
+    got = {}
+    for faces in ("1", "0"):
+        monkeypatch.setenv("DAISY_FF_FACES", faces)
+        p = _ctx(dz, sc, uv50)
+        got[faces] = (p.cudaCalculateRadiosityMatrix().rows().copy(), p.visibilityMasks(3000, 256).copy())
+        p.close()
+    assert np.array_equal(got["1"][0].view(np.uint32), got["0"][0].view(np.uint32))
+    assert np.array_equal(got["1"][1], got["0"][1])
+
+
 def test_edge_heavy_pattern_and_coplanar_decal_vs_bruteforce(dz):
     """Stress for the skipping premises, against the brute-force oracle (every ray against every triangle):
     * a sample pattern with samples ON the triangle edges and vertices (u = 0, v = 0, u + v = 1) next to random ones --
