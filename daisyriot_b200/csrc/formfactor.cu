@@ -403,45 +403,26 @@ __device__ __forceinline__ bool shaft_box(const Shaft &s, float lox, float loy, 
 // carries the plane id common to all triangles below it, whole subtrees of a wall the pair starts or ends on are never
 // entered.  Returns the number of candidates, or -1 if they do not fit SHAFT_CAP.
 //
-// Face grids (faces.cu): a child whose triangles all lie in face f (plane id f + 1 <= nfaces) is not entered either when every
-// ray of the pair meets that plane at |cos| >= FACE_COS_MIN -- the face goes into the pair's face mask instead and the rays
-// look their crossing up in the face's grid (pair_mask_warp).  The bound is the one of pair_premise: the ray directions are
-// convex combinations of the three vertex-to-vertex vectors D_i, so n.D_i of one sign gives cos >= min|n.D_i| / max|D_i|.
-#define FACE_COS_MIN 0.05f
+// Face grids (faces.cu): a child whose triangles all lie in face f (plane id f + 1 <= nfaces) is not entered either: the face
+// goes into the pair's face mask and every ray settles it on its own (pair_mask_warp: plane crossing + cell lookup, or proof
+// that it stays clear of the plane, or -- for the few rays that graze the plane -- a walk restricted to that face).
 __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, int root, const Shaft &sh, int skip_lo, int skip_hi, int lo, int hi,
-                                                int *__restrict__ cand, const TriVerts &A, const TriVerts &B, const DzFace *__restrict__ faces, int nfaces,
-                                                unsigned long long &fmask) {
+                                                int *__restrict__ cand, int nfaces, unsigned long long &fmask) {
     int n_main = 0;
     int stack[64];
     int sp = 0;
     int cur = root;
     bool overflow = false;
-    unsigned long long ftested = 0;
     fmask = 0;
     if (cur < 0) return 0; // single-triangle hierarchy: no third triangle exists
-    auto face_ok = [&](int p) -> bool {
-        const unsigned long long bit = 1ull << (p - 1);
-        if (ftested & bit) return (fmask & bit) != 0;
-        ftested |= bit;
-        const float4 pl = __ldg(&faces[p - 1].pl);
-        const float d0x = B.a.x - A.a.x, d0y = B.a.y - A.a.y, d0z = B.a.z - A.a.z;
-        const float d1x = B.b.x - A.b.x, d1y = B.b.y - A.b.y, d1z = B.b.z - A.b.z;
-        const float d2x = B.c.x - A.c.x, d2y = B.c.y - A.c.y, d2z = B.c.z - A.c.z;
-        const float dm2 = fmaxf(d0x * d0x + d0y * d0y + d0z * d0z, fmaxf(d1x * d1x + d1y * d1y + d1z * d1z, d2x * d2x + d2y * d2y + d2z * d2z));
-        const float l0 = pl.x * d0x + pl.y * d0y + pl.z * d0z, l1 = pl.x * d1x + pl.y * d1y + pl.z * d1z, l2 = pl.x * d2x + pl.y * d2y + pl.z * d2z;
-        const float lmin = fminf(fabsf(l0), fminf(fabsf(l1), fabsf(l2)));
-        const bool ok = (l0 > 0.f) == (l1 > 0.f) && (l1 > 0.f) == (l2 > 0.f) && lmin * lmin >= (FACE_COS_MIN * FACE_COS_MIN) * dm2 && dm2 > 0.f;
-        if (ok) fmask |= bit;
-        return ok;
-    };
     while (!overflow) {
         const BvhNode nd = nodes[cur];
         const bool sl = nd.d.z != 0 && (nd.d.z == skip_lo || nd.d.z == skip_hi);
         const bool sr = nd.d.w != 0 && (nd.d.w == skip_lo || nd.d.w == skip_hi);
         bool hl = !sl && shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
         bool hr = !sr && shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
-        if (hl && nd.d.z > 0 && nd.d.z <= nfaces && face_ok(nd.d.z)) hl = false;
-        if (hr && nd.d.w > 0 && nd.d.w <= nfaces && face_ok(nd.d.w)) hr = false;
+        if (hl && nd.d.z > 0 && nd.d.z <= nfaces) { fmask |= 1ull << (nd.d.z - 1); hl = false; }
+        if (hr && nd.d.w > 0 && nd.d.w <= nfaces) { fmask |= 1ull << (nd.d.w - 1); hr = false; }
         if (hl && nd.d.x < 0) {
             const int k = ~nd.d.x;
             if (k != lo && k != hi) { DZ_ASSERT(k >= 0 && n_main <= SHAFT_CAP); if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
@@ -492,11 +473,56 @@ __device__ __forceinline__ void pair_premise(const TriVerts &A, const TriVerts &
 // watertight test.  Same predicate as ray_sees: sample i sees hi iff hi is accepted at t_hi and no other triangle k
 // is accepted with (t_k, k) < (t_hi, hi); lo takes part like any other triangle.  The main list is tested by every
 // sample, the ring list (coplanar with lo or hi, see shaft_candidates) only by the edge samples.
+#define FACE_COS_MIN 0.05f
 struct FaceTables {
     const DzFace *faces;
     const int *cells, *lists;
-    float tm; // margin on the ray parameter: crossings within tm of either end point are resolved by explicit tests
+    const BvhNode *nodes;
+    int root;
+    float tm;  // margin on the ray parameter: crossings within tm of either end point are resolved by explicit tests
+    float eps; // a ray can only touch a triangle of a face where it runs within eps of the face's plane
 };
+
+// Is the ray blocked by a triangle of plane id fpid?  LBVH walk that enters only children holding such triangles (their own
+// id, or 0 = mixed) -- the exact test for the few rays that run along a face's plane too flatly for the grid lookup.
+__device__ __noinline__ bool face_blocks_ray(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root, const WRay &w, f3 dir, float thi,
+                                             int lo, int hi, int fpid) {
+    const f3 o = w.o;
+    const f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
+    int stack[64];
+    int sp = 0, cur = root;
+    if (cur < 0) return false;
+    while (true) {
+        const BvhNode nd = nodes[cur];
+        float tl, tr, tk, uu, vv;
+        bool hl = (nd.d.z == 0 || nd.d.z == fpid) && ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, thi, tl);
+        bool hr = (nd.d.w == 0 || nd.d.w == fpid) && ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, thi, tr);
+        if (hl && nd.d.x < 0) {
+            const int k = ~nd.d.x;
+            if (nd.d.z == fpid && k != lo && k != hi) {
+                const TriVerts t = tv[k];
+                if (wray_tri_sel(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return true;
+            }
+            hl = false;
+        }
+        if (hr && nd.d.y < 0) {
+            const int k = ~nd.d.y;
+            if (nd.d.w == fpid && k != lo && k != hi) {
+                const TriVerts t = tv[k];
+                if (wray_tri_sel(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return true;
+            }
+            hr = false;
+        }
+        if (hl && hr) { DZ_ASSERT(sp < 64); stack[sp++] = nd.d.y; cur = nd.d.x; }
+        else if (hl) cur = nd.d.x;
+        else if (hr) cur = nd.d.y;
+        else {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    return false;
+}
 __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox,
                                                    const TriVerts &Tlo, const TriVerts &Thi, int lo, int hi, const int *cand,
                                                    int n_main, unsigned long long fmask, const FaceTables &ft, const int *nbr_lo, const int *nbr_hi, int n_inner,
@@ -527,8 +553,55 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 const float4 pl = __ldg(&ft.faces[f].pl);
                 const float ndir = pl.x * dir.x + pl.y * dir.y + pl.z * dir.z;
                 const float norg = pl.x * o.x + pl.y * o.y + pl.z * o.z;
-                const float t = __fdividef(pl.w - norg, ndir);
-                if (alive && t > -ft.tm && t < thi + ft.tm) {
+                const float s0 = norg - pl.w; // signed distance of the origin
+                if (alive && fabsf(ndir) < FACE_COS_MIN) {
+                    // Flat ray: it can only touch triangles of the face where it runs within eps of the plane.  That stretch
+                    // [ta, tb] of the ray is usually empty (both end points clear of the plane on one side) or short (the ray
+                    // leaves from / arrives on / skims the plane near one end): the lists of the few cells under it are tested.
+                    // A long stretch (a ray lying in the plane) searches the face through the LBVH.
+                    float ta = 0.f, tb = -1.f;
+                    if (fabsf(ndir) > 1e-12f) {
+                        const float r = __fdividef(1.0f, ndir), tc = -s0 * r, hw = ft.eps * fabsf(r);
+                        ta = fmaxf(tc - hw, 0.f); tb = fminf(tc + hw, thi);
+                    } else if (fabsf(s0) <= ft.eps) tb = thi;
+                    if (ta <= tb) {
+                        const float4 ex = __ldg(&ft.faces[f].ex), ey = __ldg(&ft.faces[f].ey);
+                        const int4 g = __ldg(&ft.faces[f].g);
+                        const float Xa = fmaf(ta, dir.x, o.x), Ya = fmaf(ta, dir.y, o.y), Za = fmaf(ta, dir.z, o.z);
+                        const float Xb = fmaf(tb, dir.x, o.x), Yb = fmaf(tb, dir.y, o.y), Zb = fmaf(tb, dir.z, o.z);
+                        const float a0 = fmaf(Xa, ex.x, fmaf(Ya, ex.y, fmaf(Za, ex.z, ex.w))), b0 = fmaf(Xa, ey.x, fmaf(Ya, ey.y, fmaf(Za, ey.z, ey.w)));
+                        const float a1 = fmaf(Xb, ex.x, fmaf(Yb, ex.y, fmaf(Zb, ex.z, ex.w))), b1 = fmaf(Xb, ey.x, fmaf(Yb, ey.y, fmaf(Zb, ey.z, ey.w)));
+                        const int ia0 = max(0, (int)floorf(fminf(a0, a1))), ia1 = min(g.x - 1, (int)floorf(fmaxf(a0, a1)));
+                        const int ib0 = max(0, (int)floorf(fminf(b0, b1))), ib1 = min(g.y - 1, (int)floorf(fmaxf(b0, b1)));
+                        if (ia0 <= ia1 && ib0 <= ib1) {
+                            if ((ia1 - ia0 + 1) * (ib1 - ib0 + 1) <= 16) {
+                                for (int ib = ib0; ib <= ib1 && alive; ib++)
+                                    for (int ia = ia0; ia <= ia1 && alive; ia++) {
+                                        const int c = __ldg(ft.cells + g.z + ib * g.x + ia);
+                                        if (c < 0) continue;
+                                        const int *L = ft.lists + (c >> 1);
+                                        const int n = __ldg(L);
+                                        for (int q = 1; q <= n; q++) {
+                                            const int k = __ldg(L + q);
+                                            if (k == lo || k == hi) continue;
+#ifdef DAISY_FF_STATS
+                                            atomicAdd(&g_ffstats[23], 1ull);
+#endif
+                                            const TriVerts tr = tv[k];
+                                            if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) { alive = false; break; }
+                                        }
+                                    }
+                            } else {
+#ifdef DAISY_FF_STATS
+                                atomicAdd(&g_ffstats[19], 1ull);
+#endif
+                                if (face_blocks_ray(ft.nodes, tv, ft.root, w, dir, thi, lo, hi, f + 1)) alive = false;
+                            }
+                        }
+                    }
+                }
+                const float t = __fdividef(-s0, ndir);
+                if (alive && fabsf(ndir) >= FACE_COS_MIN && t > -ft.tm && t < thi + ft.tm) {
                     const float4 ex = __ldg(&ft.faces[f].ex), ey = __ldg(&ft.faces[f].ey);
                     const int4 g = __ldg(&ft.faces[f].g);
                     const float X = fmaf(t, dir.x, o.x), Y = fmaf(t, dir.y, o.y), Z = fmaf(t, dir.z, o.z);
@@ -887,6 +960,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
         };
         FaceTables ftab;
         ftab.faces = P.faces; ftab.cells = P.face_cells; ftab.lists = P.face_lists; ftab.tm = P.face_tm;
+        ftab.nodes = P.nodes; ftab.root = P.root; ftab.eps = 0.0625f * P.face_tm;
         while (true) { // 2a
             int q0 = 0;
             if (lane == 0) q0 = atomicAdd(&s_next, 32);
@@ -912,8 +986,8 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
                 bool on_lo = false, on_hi = false;
                 if (P.ring_on) pair_premise(A, B, sm.pl[ilo], sm.pl[ihi], on_lo, on_hi, m_req);
-                ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand, A, B,
-                                         P.faces, P.nfaces, fmask);
+                ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand,
+                                         P.nfaces, fmask);
                 if (ncand >= 0) ncand |= (on_lo ? 0x10000 : 0) | (on_hi ? 0x20000 : 0);
                 if (ncand < 0) { // the lists do not fit: flag the pair, phase 2b walks the LBVH per ray
                     s_list[q] = (unsigned short)(idx | PAIR_HEAVY);
@@ -1122,8 +1196,8 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
         for (int c = 0; c < 4; c++)
             fprintf(stderr, "ffstats %-18s pairs %12llu  mean n_main %7.1f  mean n_ring %6.1f\n", nm[c], h[c], h[c] ? (double)h[4 + c] / h[c] : 0.0, h[c] ? (double)h[8 + c] / h[c] : 0.0);
         fprintf(stderr, "ffstats simple&fully-visible %llu ; slab iterations pass0 %llu pass1 %llu\n", h[12], h[16], h[17]);
-        fprintf(stderr, "ffstats faces: %d grids, face entries over all pairs %llu, pairs with neither list nor face %llu, cell lookups %llu, explicit tests in cells %llu\n",
-                ctx->nfaces, h[13], h[18], h[15], h[14]);
+        fprintf(stderr, "ffstats faces: %d grids, face entries over all pairs %llu, pairs with neither list nor face %llu, cell lookups %llu, explicit tests in cells %llu, flat-ray tests in cells %llu, rays searching a face %llu\n",
+                ctx->nfaces, h[13], h[18], h[15], h[14], h[23], h[19]);
         fprintf(stderr, "ffstats flush: rounds executed %llu, rounds if balanced over lanes %llu, tests queued %llu (%.1f lanes per executed round)\n",
                 h[22], h[20], h[21], h[22] ? (double)h[21] / h[22] : 0.0);
         {
