@@ -130,7 +130,7 @@ __global__ void k_hierarchy(const uint64_t *__restrict__ keys, int N, int2 *__re
 // bottom-up refit: the second thread to arrive at a node merges its two children and moves on
 __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__restrict__ tv, int N, float pad,
                         const int2 *__restrict__ children, const int *__restrict__ parent, float *__restrict__ box /* (2N-1) x 6 */,
-                        int *__restrict__ flags, float4 *__restrict__ tribox, const int *__restrict__ pid, int *__restrict__ spid /* 2N-1 */) {
+                        int *__restrict__ flags, float4 *__restrict__ tribox, const int *__restrict__ pid, int *__restrict__ spid /* 2N-1 */, int nfaces) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N) return;
     int tri = (int)(uint32_t)keys[p];
@@ -161,7 +161,10 @@ __global__ void k_refit(const uint64_t *__restrict__ keys, const TriVerts *__res
         {
             volatile int *vs = spid;
             const int sl = vs[l], sr = vs[r];
-            spid[node] = (sl == sr) ? sl : 0;
+            // -1: nothing but triangles of gridded faces below (ids 1..nfaces, several of them): the shaft walk of the
+            // form-factor kernel never enters such a subtree, faces are found through their own boxes
+            const bool fl = sl == -1 || (sl >= 1 && sl <= nfaces), fr = sr == -1 || (sr >= 1 && sr <= nfaces);
+            spid[node] = (sl == sr) ? sl : ((fl && fr) ? -1 : 0);
         }
         __threadfence();
         node = parent[node];
@@ -183,7 +186,7 @@ __global__ void k_pack_nodes(const uint64_t *__restrict__ keys, int N, const int
     // leaves refer to the ORIGINAL triangle id
     int li = ch.x >= 0 ? ch.x : ~(int)(uint32_t)keys[~ch.x];
     int ri = ch.y >= 0 ? ch.y : ~(int)(uint32_t)keys[~ch.y];
-    n.d = make_int4(li, ri, spid[l], spid[r]); // plane id common to everything below each child (leaf: the triangle's own), 0 = mixed
+    n.d = make_int4(li, ri, spid[l], spid[r]); // plane id common to everything below each child (leaf: the triangle's own), 0 = mixed, -1 = mixed but gridded faces only
     nodes[i] = n;
 }
 
@@ -233,7 +236,7 @@ int dz_build_lbvh(daisy_ctx *ctx) {
     if (N > 1) {
         k_hierarchy<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_parent);
     }
-    k_refit<<<(N + 255) / 256, 256, 0, st>>>(d_keys, ctx->d_triverts, N, ctx->pad, d_children, d_parent, d_box, d_flags, ctx->d_tribox, ctx->d_pid, d_spid);
+    k_refit<<<(N + 255) / 256, 256, 0, st>>>(d_keys, ctx->d_triverts, N, ctx->pad, d_children, d_parent, d_box, d_flags, ctx->d_tribox, ctx->d_pid, d_spid, ctx->nfaces);
     if (N > 1) {
         k_pack_nodes<<<(N - 1 + 255) / 256, 256, 0, st>>>(d_keys, N, d_children, d_box, d_spid, ctx->d_nodes);
         ctx->root = 0;

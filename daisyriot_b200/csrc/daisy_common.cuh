@@ -187,7 +187,7 @@ struct __align__(16) BvhNode {
     float4 a; // L.lo.x L.lo.y L.lo.z L.hi.x
     float4 b; // L.hi.y L.hi.z R.lo.x R.lo.y
     float4 c; // R.lo.z R.hi.x R.hi.y R.hi.z
-    int4 d;   // left, right, plane id shared by every triangle below the left child (0 = mixed / none), same for the right child
+    int4 d;   // left, right, plane id shared by every triangle below the left child (0 = mixed / none, -1 = mixed, gridded faces only), same for the right child
 };
 
 // conservative slab test against [0, tmax]; boxes are padded at build time, fminf/fmaxf drop the NaN of 0*inf
@@ -234,6 +234,7 @@ struct __align__(16) DzFace {
     float4 ex; // in-plane axis / cell size, offset
     float4 ey;
     int4 g;    // nx, ny, index of the face's first cell in the cell table, number of triangles
+    float4 blo, bhi; // padded bounding box of the face's triangles
 };
 
 __device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }

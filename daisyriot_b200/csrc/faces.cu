@@ -32,7 +32,7 @@
 
 #define FACE_MIN_TRIS 32
 #define FACE_DELTA 2.5e-4     // x scene extent
-#define FACE_CELLS_PER_TRI 4.0
+#define FACE_CELLS_PER_TRI 16.0
 #define FACE_MAX_CELLS (1 << 22)
 #define FACE_PLANE_TOL 1.2e-6 // x scene extent: members farther than this from the refitted plane => no grid for the face
 
@@ -275,6 +275,15 @@ int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, 
                 F.ex = make_float4((float)(ex.x / cs), (float)(ex.y / cs), (float)(ex.z / cs), (float)(-(dot3(c0, ex) + A0) / cs));
                 F.ey = make_float4((float)(ey.x / cs), (float)(ey.y / cs), (float)(ey.z / cs), (float)(-(dot3(c0, ey) + B0) / cs));
                 F.g = make_int4(nx, ny, cell_base, (int)mem.size());
+                float blo[3] = { INFINITY, INFINITY, INFINITY }, bhi[3] = { -INFINITY, -INFINITY, -INFINITY };
+                for (int t : mem)
+                    for (int k = 0; k < 3; k++)
+                        for (int dd = 0; dd < 3; dd++) {
+                            const float v = vertices[3 * (size_t)tri_idx[6 * (size_t)t + k] + dd];
+                            blo[dd] = fminf(blo[dd], v); bhi[dd] = fmaxf(bhi[dd], v);
+                        }
+                F.blo = make_float4(blo[0] - c->pad, blo[1] - c->pad, blo[2] - c->pad, 0.f);
+                F.bhi = make_float4(bhi[0] + c->pad, bhi[1] + c->pad, bhi[2] + c->pad, 0.f);
                 faces.push_back(F);
                 face_group.push_back(g);
             }

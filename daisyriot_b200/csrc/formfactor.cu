@@ -403,26 +403,31 @@ __device__ __forceinline__ bool shaft_box(const Shaft &s, float lox, float loy, 
 // carries the plane id common to all triangles below it, whole subtrees of a wall the pair starts or ends on are never
 // entered.  Returns the number of candidates, or -1 if they do not fit SHAFT_CAP.
 //
-// Face grids (faces.cu): a child whose triangles all lie in face f (plane id f + 1 <= nfaces) is not entered either: the face
-// goes into the pair's face mask and every ray settles it on its own (pair_mask_warp: plane crossing + cell lookup, or proof
-// that it stays clear of the plane, or -- for the few rays that graze the plane -- a walk restricted to that face).
+// Face grids (faces.cu): a child that holds nothing but triangles of gridded faces (plane ids 1..nfaces; the node carries
+// the id, or -1 for several faces) is not entered either.  The faces a pair has to consider are found by testing the faces'
+// own boxes against the shaft (they are at most DAISY_MAX_FACES); each goes into the pair's face mask and every ray settles
+// it on its own (pair_mask_warp: plane crossing + cell lookup, or proof that it stays clear of the plane, or -- for the few
+// rays that lie in the plane -- a walk restricted to that face).  In a scene made of planar faces only, the walk ends at the root.
 __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ nodes, int root, const Shaft &sh, int skip_lo, int skip_hi, int lo, int hi,
-                                                int *__restrict__ cand, int nfaces, unsigned long long &fmask) {
+                                                int *__restrict__ cand, const DzFace *__restrict__ faces, int nfaces, unsigned long long &fmask) {
     int n_main = 0;
     int stack[64];
     int sp = 0;
     int cur = root;
     bool overflow = false;
     fmask = 0;
+    for (int f = 0; f < nfaces; f++) {
+        if (f + 1 == skip_lo || f + 1 == skip_hi) continue;
+        const float4 b0 = __ldg(&faces[f].blo), b1 = __ldg(&faces[f].bhi);
+        if (shaft_box(sh, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z)) fmask |= 1ull << f;
+    }
     if (cur < 0) return 0; // single-triangle hierarchy: no third triangle exists
     while (!overflow) {
         const BvhNode nd = nodes[cur];
-        const bool sl = nd.d.z != 0 && (nd.d.z == skip_lo || nd.d.z == skip_hi);
-        const bool sr = nd.d.w != 0 && (nd.d.w == skip_lo || nd.d.w == skip_hi);
+        const bool sl = nd.d.z != 0 && (nd.d.z == skip_lo || nd.d.z == skip_hi || nd.d.z == -1 || nd.d.z <= nfaces);
+        const bool sr = nd.d.w != 0 && (nd.d.w == skip_lo || nd.d.w == skip_hi || nd.d.w == -1 || nd.d.w <= nfaces);
         bool hl = !sl && shaft_box(sh, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y);
         bool hr = !sr && shaft_box(sh, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w);
-        if (hl && nd.d.z > 0 && nd.d.z <= nfaces) { fmask |= 1ull << (nd.d.z - 1); hl = false; }
-        if (hr && nd.d.w > 0 && nd.d.w <= nfaces) { fmask |= 1ull << (nd.d.w - 1); hr = false; }
         if (hl && nd.d.x < 0) {
             const int k = ~nd.d.x;
             if (k != lo && k != hi) { DZ_ASSERT(k >= 0 && n_main <= SHAFT_CAP); if (n_main == SHAFT_CAP) overflow = true; else cand[n_main++] = k; }
@@ -484,7 +489,7 @@ struct FaceTables {
 };
 
 // Is the ray blocked by a triangle of plane id fpid?  LBVH walk that enters only children holding such triangles (their own
-// id, or 0 = mixed) -- the exact test for the few rays that run along a face's plane too flatly for the grid lookup.
+// id, or 0 / -1 = mixed) -- the exact test for the few rays that run along a face's plane too flatly for the grid lookup.
 __device__ __noinline__ bool face_blocks_ray(const BvhNode *__restrict__ nodes, const TriVerts *__restrict__ tv, int root, const WRay &w, f3 dir, float thi,
                                              int lo, int hi, int fpid) {
     const f3 o = w.o;
@@ -495,8 +500,8 @@ __device__ __noinline__ bool face_blocks_ray(const BvhNode *__restrict__ nodes, 
     while (true) {
         const BvhNode nd = nodes[cur];
         float tl, tr, tk, uu, vv;
-        bool hl = (nd.d.z == 0 || nd.d.z == fpid) && ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, thi, tl);
-        bool hr = (nd.d.w == 0 || nd.d.w == fpid) && ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, thi, tr);
+        bool hl = (nd.d.z <= 0 || nd.d.z == fpid) && ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, thi, tl);
+        bool hr = (nd.d.w <= 0 || nd.d.w == fpid) && ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, thi, tr);
         if (hl && nd.d.x < 0) {
             const int k = ~nd.d.x;
             if (nd.d.z == fpid && k != lo && k != hi) {
@@ -574,16 +579,27 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                         const int ia0 = max(0, (int)floorf(fminf(a0, a1))), ia1 = min(g.x - 1, (int)floorf(fmaxf(a0, a1)));
                         const int ib0 = max(0, (int)floorf(fminf(b0, b1))), ib1 = min(g.y - 1, (int)floorf(fmaxf(b0, b1)));
                         if (ia0 <= ia1 && ib0 <= ib1) {
-                            if ((ia1 - ia0 + 1) * (ib1 - ib0 + 1) <= 16) {
-                                for (int ib = ib0; ib <= ib1 && alive; ib++)
-                                    for (int ia = ia0; ia <= ia1 && alive; ia++) {
+                            if ((ia1 - ia0) + (ib1 - ib0) <= 40) {
+                                // the cells under the stretch, column by column (the b-range of the stretch inside a column, widened
+                                // by a hundredth of a cell); a triangle tested a moment ago is not tested again
+                                const float da = a1 - a0, rda = (fabsf(da) > 1e-6f) ? __fdividef(b1 - b0, da) : 0.f;
+                                int prev1 = -1, prev2 = -1;
+                                for (int ia = ia0; ia <= ia1 && alive; ia++) {
+                                    int jb0 = ib0, jb1 = ib1;
+                                    if (ia0 != ia1 && fabsf(da) > 1e-6f) {
+                                        const float ca0 = fminf(fmaxf((float)ia, fminf(a0, a1)), fmaxf(a0, a1)), ca1 = fminf(fmaxf((float)(ia + 1), fminf(a0, a1)), fmaxf(a0, a1));
+                                        const float cb0 = fmaf(ca0 - a0, rda, b0), cb1 = fmaf(ca1 - a0, rda, b0);
+                                        jb0 = max(ib0, (int)floorf(fminf(cb0, cb1) - 0.01f)); jb1 = min(ib1, (int)floorf(fmaxf(cb0, cb1) + 0.01f));
+                                    }
+                                    for (int ib = jb0; ib <= jb1 && alive; ib++) {
                                         const int c = __ldg(ft.cells + g.z + ib * g.x + ia);
                                         if (c < 0) continue;
                                         const int *L = ft.lists + (c >> 1);
                                         const int n = __ldg(L);
                                         for (int q = 1; q <= n; q++) {
                                             const int k = __ldg(L + q);
-                                            if (k == lo || k == hi) continue;
+                                            if (k == lo || k == hi || k == prev1 || k == prev2) continue;
+                                            prev2 = prev1; prev1 = k;
 #ifdef DAISY_FF_STATS
                                             atomicAdd(&g_ffstats[23], 1ull);
 #endif
@@ -591,6 +607,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                                             if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) { alive = false; break; }
                                         }
                                     }
+                                }
                             } else {
 #ifdef DAISY_FF_STATS
                                 atomicAdd(&g_ffstats[19], 1ull);
@@ -634,20 +651,28 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 any = __any_sync(0xffffffffu, alive);
             }
         }
-        // reciprocal direction, kept finite: with inv = inf the pre-multiplied form would turn a box that straddles 0 on an
-        // axis the ray is parallel to into (-inf, NaN) and reject it
-        f3 inv = mk3(1.0f / (fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x)), 1.0f / (fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y)),
-                     1.0f / (fabsf(dir.z) > 1e-30f ? dir.z : copysignf(1e-30f, dir.z)));
-        f3 oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-        // Slab tests run in lock step over the list (uniform box loads); a lane that passes one only QUEUES the
-        // triangle.  The expensive watertight tests are then issued for whole queues at a time, so a warp instruction
-        // slot is spent on them only when many lanes have one pending, not whenever a single lane does.
-        // do all rays of this pass enter every box through the same three planes?  (same signs of the direction components)
-        const unsigned act = __ballot_sync(0xffffffffu, i < S);
-        const unsigned bx = __ballot_sync(0xffffffffu, i < S && inv.x < 0.f), by = __ballot_sync(0xffffffffu, i < S && inv.y < 0.f),
-                       bz = __ballot_sync(0xffffffffu, i < S && inv.z < 0.f);
-        const bool neg_x = bx != 0, neg_y = by != 0, neg_z = bz != 0;
-        const bool sorted = (bx == 0 || bx == act) && (by == 0 || by == act) && (bz == 0 || bz == act);
+        // neighbour lists are needed by the samples closer to an edge than the pair's required margin (see below)
+        unsigned edge = 0;
+        if ((nbr_lo || nbr_hi) && pass * 32 + 31 >= n_inner) edge = __ballot_sync(0xffffffffu, alive && i >= n_inner && fminf(fminf(u, v), 1.0f - u - v) < m_req);
+        // reciprocal direction (only the slab tests of the candidate list and of the neighbour lists use it), kept finite: with
+        // inv = inf the pre-multiplied form would turn a box that straddles 0 on an axis the ray is parallel to into (-inf, NaN)
+        // and reject it
+        f3 inv = mk3(0.f, 0.f, 0.f), oi = inv;
+        bool neg_x = false, neg_y = false, neg_z = false, sorted = false;
+        if (n_main > 0 || edge) {
+            inv = mk3(1.0f / (fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x)), 1.0f / (fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y)),
+                      1.0f / (fabsf(dir.z) > 1e-30f ? dir.z : copysignf(1e-30f, dir.z)));
+            oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+            // Slab tests run in lock step over the list (uniform box loads); a lane that passes one only QUEUES the
+            // triangle.  The expensive watertight tests are then issued for whole queues at a time, so a warp instruction
+            // slot is spent on them only when many lanes have one pending, not whenever a single lane does.
+            // do all rays of this pass enter every box through the same three planes?  (same signs of the direction components)
+            const unsigned act = __ballot_sync(0xffffffffu, i < S);
+            const unsigned bx = __ballot_sync(0xffffffffu, i < S && inv.x < 0.f), by = __ballot_sync(0xffffffffu, i < S && inv.y < 0.f),
+                           bz = __ballot_sync(0xffffffffu, i < S && inv.z < 0.f);
+            neg_x = bx != 0; neg_y = by != 0; neg_z = bz != 0;
+            sorted = (bx == 0 || bx == act) && (by == 0 || by == act) && (bz == 0 || bz == act);
+        }
         int qlen = 0;
         unsigned qreg = 0; // queued candidates: 4-bit positions inside the staged chunk of 16
         auto flush = [&]() {
@@ -715,9 +740,8 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         // Neighbour lists (triangles in the plane of lo / hi next to the patch, null if that side's premise does not hold):
         // only samples closer to an edge of their triangles than the pair's required margin have to test them.  They are few
         // (usually 0-3 of 50), so the roles flip: the edge sample's ray is broadcast and lane = neighbour.
-        if ((nbr_lo || nbr_hi) && pass * 32 + 31 >= n_inner) {
-            const float mg = fminf(fminf(u, v), 1.0f - u - v);
-            unsigned edge = __ballot_sync(0xffffffffu, alive && i >= n_inner && mg < m_req);
+        {
+            edge &= __ballot_sync(0xffffffffu, alive); // the candidate list may have settled some of them meanwhile
             if (edge) {
                 // lane < n_lo: neighbour of lo; n_lo <= lane < n_lo + n_hi: neighbour of hi (NBR_CAP - 1 <= 31 each: two rounds at most)
                 const int n_lo = nbr_lo ? __ldg(nbr_lo) : 0, n_hi = nbr_hi ? __ldg(nbr_hi) : 0;
@@ -987,7 +1011,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 bool on_lo = false, on_hi = false;
                 if (P.ring_on) pair_premise(A, B, sm.pl[ilo], sm.pl[ihi], on_lo, on_hi, m_req);
                 ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand,
-                                         P.nfaces, fmask);
+                                         P.faces, P.nfaces, fmask);
                 if (ncand >= 0) ncand |= (on_lo ? 0x10000 : 0) | (on_hi ? 0x20000 : 0);
                 if (ncand < 0) { // the lists do not fit: flag the pair, phase 2b walks the LBVH per ray
                     s_list[q] = (unsigned short)(idx | PAIR_HEAVY);
@@ -1153,7 +1177,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     P.order = ctx->d_order;
     P.plane = ctx->d_plane; P.pid = ctx->d_pid; P.nbr = ctx->d_nbr; P.n_inner = ctx->n_nonedge;
     P.faces = ctx->d_faces; P.face_cells = ctx->d_face_cells; P.face_lists = ctx->d_face_lists; P.nfaces = ctx->nfaces; P.face_tm = 4.0f * ctx->pad;
-    { const char *e = getenv("DAISY_FF_FACES"); if (e && e[0] == '0') P.nfaces = 0; }
+
     { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
