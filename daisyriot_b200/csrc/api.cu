@@ -215,6 +215,28 @@ extern "C" int daisy_plane_ids(const float *vertices, int nv, const int32_t *tri
     return DAISY_OK;
 }
 
+int dz_face_grid_stats(float ext, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid, int max_faces, int64_t *out6, int *nfaces_out); // faces.cu
+extern "C" int daisy_face_grid_stats(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int max_faces, int64_t *stats6, int32_t *nfaces_out, int32_t *pid_out) {
+    DZ_REQUIRE(ntri >= 0 && nv >= 0 && max_faces >= 0 && nfaces_out && (ntri == 0 || (vertices && tri_idx)), DAISY_E_INVALID, "daisy_face_grid_stats: bad argument");
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int i = 0; i < ntri; i++)
+        for (int k = 0; k < 3; k++) {
+            const int v = tri_idx[6 * (size_t)i + k];
+            DZ_REQUIRE(v >= 0 && v < nv, DAISY_E_INVALID, "daisy_face_grid_stats: triangle index out of range");
+            for (int d = 0; d < 3; d++) { lo[d] = fminf(lo[d], vertices[3 * (size_t)v + d]); hi[d] = fmaxf(hi[d], vertices[3 * (size_t)v + d]); }
+        }
+    float ext = 0.f;
+    for (int d = 0; d < 3; d++) if (ntri) ext = fmaxf(ext, hi[d] - lo[d]);
+    std::vector<int> pid;
+    assign_plane_ids(vertices, tri_idx, ntri, ext, pid);
+    int nf = 0;
+    const int rc = dz_face_grid_stats(ext, vertices, tri_idx, ntri, pid, max_faces, stats6, &nf);
+    if (rc) return rc;
+    *nfaces_out = nf;
+    if (pid_out) for (int i = 0; i < ntri; i++) pid_out[i] = pid[(size_t)i];
+    return DAISY_OK;
+}
+
 static void set_partition(daisy_ctx *c, int rank, int nranks) {
     c->rank = rank; c->nranks = nranks;
     int n = (c->N + nranks - 1) / nranks;

@@ -108,11 +108,12 @@ void dz_free_faces(daisy_ctx *c) {
 // Chooses the faces, renumbers `pid` so that face f carries plane id f + 1 (all other groups keep distinct ids above the
 // faces'), builds the grids and uploads them.  A face whose grid cannot be built is simply left out (its triangles stay
 // ordinary candidates): nothing here can make a result wrong, only slower.
-int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid) {
-    c->nfaces = 0;
-    if (ntri == 0 || !(c->ext > 0.f)) return DAISY_OK;
+static int build_face_tables(float ext_f, float pad, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid,
+                             std::vector<DzFace> &faces, std::vector<int> &cells, std::vector<int> &lists) {
+    faces.clear(); cells.clear(); lists.clear();
+    if (ntri == 0 || !(ext_f > 0.f)) return DAISY_OK;
     { const char *e = getenv("DAISY_FF_FACES"); if (e && e[0] == '0') return DAISY_OK; }
-    const double ext = (double)c->ext, delta = FACE_DELTA * ext;
+    const double ext = (double)ext_f, delta = FACE_DELTA * ext;
     int maxid = 0;
     for (int t = 0; t < ntri; t++) maxid = std::max(maxid, pid[(size_t)t]);
     std::vector<std::vector<int>> members((size_t)maxid + 1);
@@ -127,8 +128,7 @@ int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, 
         const float *p = vertices + 3 * (size_t)tri_idx[6 * (size_t)t + k];
         return { (double)p[0], (double)p[1], (double)p[2] };
     };
-    std::vector<DzFace> faces;
-    std::vector<int> cells, lists, face_group;
+    std::vector<int> face_group;
     std::vector<double> pts;
     for (int g : order) {
         if ((int)faces.size() == DAISY_MAX_FACES) break;
@@ -282,8 +282,8 @@ int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, 
                             const float v = vertices[3 * (size_t)tri_idx[6 * (size_t)t + k] + dd];
                             blo[dd] = fminf(blo[dd], v); bhi[dd] = fmaxf(bhi[dd], v);
                         }
-                F.blo = make_float4(blo[0] - c->pad, blo[1] - c->pad, blo[2] - c->pad, 0.f);
-                F.bhi = make_float4(bhi[0] + c->pad, bhi[1] + c->pad, bhi[2] + c->pad, 0.f);
+                F.blo = make_float4(blo[0] - pad, blo[1] - pad, blo[2] - pad, 0.f);
+                F.bhi = make_float4(bhi[0] + pad, bhi[1] + pad, bhi[2] + pad, 0.f);
                 faces.push_back(F);
                 face_group.push_back(g);
             }
@@ -299,6 +299,15 @@ int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, 
             if (!newid[(size_t)g] && !members[(size_t)g].empty()) newid[(size_t)g] = next++;
         for (int t = 0; t < ntri; t++) pid[(size_t)t] = newid[(size_t)pid[(size_t)t]];
     }
+    return DAISY_OK;
+}
+
+int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid) {
+    c->nfaces = 0;
+    std::vector<DzFace> faces;
+    std::vector<int> cells, lists;
+    const int rc = build_face_tables(c->ext, c->pad, vertices, tri_idx, ntri, pid, faces, cells, lists);
+    if (rc) return rc;
     if (faces.empty()) return DAISY_OK;
     DZ_CUDA(cudaMalloc(&c->d_faces, sizeof(DzFace) * faces.size()));
     DZ_CUDA(cudaMalloc(&c->d_face_cells, sizeof(int) * cells.size()));
@@ -309,5 +318,27 @@ int dz_build_faces(daisy_ctx *c, const float *vertices, const int32_t *tri_idx, 
     c->nfaces = (int)faces.size();
     c->face_cells = (int64_t)cells.size();
     c->face_list_ints = (int64_t)lists.size();
+    return DAISY_OK;
+}
+
+// Host-only view of the grids for tests and diagnostics: per face the numbers of triangles, cells, empty / covered / mixed
+// cells and list entries (6 int64 each), plus the renumbered plane ids.  No GPU involved.
+int dz_face_grid_stats(float ext, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid, int max_faces, int64_t *out6, int *nfaces_out) {
+    std::vector<DzFace> faces;
+    std::vector<int> cells, lists;
+    const int rc = build_face_tables(ext, 1e-4f * ext, vertices, tri_idx, ntri, pid, faces, cells, lists);
+    if (rc) return rc;
+    *nfaces_out = (int)faces.size();
+    for (size_t f = 0; f < faces.size() && (int)f < max_faces; f++) {
+        const int4 g = faces[f].g;
+        int64_t e = 0, cv = 0, mx = 0, le = 0;
+        for (int q = 0; q < g.x * g.y; q++) {
+            const int c = cells[(size_t)g.z + q];
+            if (c < 0) e++;
+            else { if (c & 1) cv++; else mx++; le += lists[(size_t)(c >> 1)]; }
+        }
+        int64_t *o = out6 + 6 * f;
+        o[0] = g.w; o[1] = (int64_t)g.x * g.y; o[2] = e; o[3] = cv; o[4] = mx; o[5] = le;
+    }
     return DAISY_OK;
 }

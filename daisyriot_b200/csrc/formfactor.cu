@@ -32,7 +32,7 @@
 __constant__ float c_uv[2 * DAISY_MAX_SAMPLES];
 __constant__ int c_perm[DAISY_MAX_SAMPLES];
 #ifdef DAISY_FF_STATS
-__device__ unsigned long long g_ffstats[32];
+__device__ unsigned long long g_ffstats[48];
 #endif
 
 int dz_set_samples_const(daisy_ctx *ctx) {
@@ -530,8 +530,8 @@ __device__ __noinline__ bool face_blocks_ray(const BvhNode *__restrict__ nodes, 
 }
 __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ tv, const float4 *__restrict__ tribox,
                                                    const TriVerts &Tlo, const TriVerts &Thi, int lo, int hi, const int *cand,
-                                                   int n_main, unsigned long long fmask, const FaceTables &ft, const int *nbr_lo, const int *nbr_hi, int n_inner,
-                                                   float m_req, const float *s_uv, const unsigned char *s_perm, int S, int lane, int *wk, float4 *wb) {
+                                                   int n_main, unsigned long long fmask, const FaceTables &ft, int own_lo, float h_lo, int own_hi, float h_hi, int own_pid_lo, int own_pid_hi,
+                                                   const int *nbr_lo, const int *nbr_hi, int n_inner, float m_req, const float *s_uv, const unsigned char *s_perm, int S, int lane, int *wk, float4 *wb) {
     unsigned mask_lo = 0, mask_hi = 0;
     for (int pass = 0; pass * 32 < S; pass++) {
         const int i = pass * 32 + lane;
@@ -549,6 +549,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         // Face grids first: one plane crossing and one cell lookup per (ray, face).  A covered cell crossed safely between the
         // ray's end points blocks the ray (some triangle of the face accepts it, faces.cu); an empty cell or a crossing beyond
         // the end points cannot; everything else runs the watertight test on the cell's own short list.
+        const float mg = fminf(fminf(u, v), 1.0f - u - v);
         if (fmask) {
             unsigned long long fm = fmask;
             bool any = __any_sync(0xffffffffu, alive);
@@ -559,7 +560,14 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                 const float ndir = pl.x * dir.x + pl.y * dir.y + pl.z * dir.z;
                 const float norg = pl.x * o.x + pl.y * o.y + pl.z * o.z;
                 const float s0 = norg - pl.w; // signed distance of the origin
-                if (alive && fabsf(ndir) < FACE_COS_MIN) {
+                // The face is the plane of lo or hi itself and the pair as a whole did not qualify for coplanar skipping (one ray
+                // is too flat, pair_premise): the premise is checked ray by ray instead -- a ray that leaves lo (reaches hi) at
+                // |cos| = |ndir| from a sample with barycentric margin mg cannot touch a coplanar neighbour once
+                // mg >= 128 eps (32 / cos) on the origin side, mg >= 128 eps (length + 64 h) / (h cos) on the far side
+                // (same bounds as pair_premise; h > 0 only for patches k_tri_planes qualified).
+                const bool act = alive && !(f == own_lo && mg * fabsf(ndir) >= 2.44e-4f) &&
+                                 !(f == own_hi && mg * fabsf(ndir) * h_hi >= 7.63e-6f * (thi + 64.f * h_hi));
+                if (act && fabsf(ndir) < FACE_COS_MIN) {
                     // Flat ray: it can only touch triangles of the face where it runs within eps of the plane.  That stretch
                     // [ta, tb] of the ray is usually empty (both end points clear of the plane on one side) or short (the ray
                     // leaves from / arrives on / skims the plane near one end): the lists of the few cells under it are tested.
@@ -570,6 +578,9 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                         ta = fmaxf(tc - hw, 0.f); tb = fminf(tc + hw, thi);
                     } else if (fabsf(s0) <= ft.eps) tb = thi;
                     if (ta <= tb) {
+#ifdef DAISY_FF_STATS
+                        atomicAdd(&g_ffstats[(f + 1 == own_pid_lo || f + 1 == own_pid_hi) ? 35 : 36], 1ull);
+#endif
                         const float4 ex = __ldg(&ft.faces[f].ex), ey = __ldg(&ft.faces[f].ey);
                         const int4 g = __ldg(&ft.faces[f].g);
                         const float Xa = fmaf(ta, dir.x, o.x), Ya = fmaf(ta, dir.y, o.y), Za = fmaf(ta, dir.z, o.z);
@@ -618,7 +629,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                     }
                 }
                 const float t = __fdividef(-s0, ndir);
-                if (alive && fabsf(ndir) >= FACE_COS_MIN && t > -ft.tm && t < thi + ft.tm) {
+                if (act && alive && fabsf(ndir) >= FACE_COS_MIN && t > -ft.tm && t < thi + ft.tm) {
                     const float4 ex = __ldg(&ft.faces[f].ex), ey = __ldg(&ft.faces[f].ey);
                     const int4 g = __ldg(&ft.faces[f].g);
                     const float X = fmaf(t, dir.x, o.x), Y = fmaf(t, dir.y, o.y), Z = fmaf(t, dir.z, o.z);
@@ -628,6 +639,11 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                         const int c = __ldg(ft.cells + g.z + (int)cb * g.x + (int)ca);
 #ifdef DAISY_FF_STATS
                         atomicAdd(&g_ffstats[15], 1ull);
+#endif
+#ifdef DAISY_FF_STATS
+                        if (c < 0) atomicAdd(&g_ffstats[38], 1ull);
+                        else if ((c & 1) && t > ft.tm && t < thi - ft.tm) atomicAdd(&g_ffstats[37], 1ull);
+                        else atomicAdd(&g_ffstats[(f + 1 == own_pid_lo || f + 1 == own_pid_hi) ? 32 : ((c & 1) ? 34 : 33)], 1ull);
 #endif
                         if (c >= 0) {
                             if ((c & 1) && t > ft.tm && t < thi - ft.tm) alive = false;
@@ -653,7 +669,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         }
         // neighbour lists are needed by the samples closer to an edge than the pair's required margin (see below)
         unsigned edge = 0;
-        if ((nbr_lo || nbr_hi) && pass * 32 + 31 >= n_inner) edge = __ballot_sync(0xffffffffu, alive && i >= n_inner && fminf(fminf(u, v), 1.0f - u - v) < m_req);
+        if ((nbr_lo || nbr_hi) && pass * 32 + 31 >= n_inner) edge = __ballot_sync(0xffffffffu, alive && i >= n_inner && mg < m_req);
         // reciprocal direction (only the slab tests of the candidate list and of the neighbour lists use it), kept finite: with
         // inv = inf the pre-multiplied form would turn a box that straddles 0 on an axis the ray is parallel to into (-inf, NaN)
         // and reject it
@@ -1021,6 +1037,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
             __syncwarp();
             FF_CLK(1);
             // (ii) lane = sample: the warp resolves its 32 pairs one after the other
+            uint64_t my_mask = 0;
             for (int j = 0; j < 32; j++) {
                 const int nc = __shfl_sync(0xffffffffu, ncand, j);
                 if (nc < 0) continue;
@@ -1032,10 +1049,11 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 const int ilo = (idj & PAIR_SWAP) ? TILE + cl : rl, ihi = (idj & PAIR_SWAP) ? rl : TILE + cl;
                 const TriVerts Tlo = s_tv[ilo], Thi = s_tv[ihi];
                 uint64_t mask = pair_mask_warp(P.tv, P.tribox, Tlo, Thi, sm.id[ilo], sm.id[ihi], warp_cand + (size_t)j * SHAFT_CAP, nc & 0xffff, fmj, ftab,
+                                               (sm.pl[ilo].w > 0.f) ? sm.pid[ilo] - 1 : -1, sm.pl[ilo].w, (sm.pl[ihi].w > 0.f) ? sm.pid[ihi] - 1 : -1, sm.pl[ihi].w, sm.pid[ilo], sm.pid[ihi],
                                                (nc & 0x10000) ? P.nbr + (size_t)sm.id[ilo] * NBR_CAP : nullptr,
                                                (nc & 0x20000) ? P.nbr + (size_t)sm.id[ihi] * NBR_CAP : nullptr, P.n_inner, mrq,
                                                sm.uv, sm.perm, P.S, lane, sm.u.p2.wk[tid >> 5], sm.u.p2.wb[tid >> 5]);
-                if (lane == 0) finish_pair(rl, cl, mask);
+                if (lane == j) my_mask = mask; // every lane holds the pair's mask: lane j keeps it and finishes its own pair below
 #ifdef DAISY_FF_STATS
                 if (lane == 0) {
                     const int nm = nc & 0xffff, pc = __popcll(mask);
@@ -1053,6 +1071,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 }
 #endif
             }
+            if (ncand >= 0) finish_pair((idx >> 6) & 63, idx & 63, my_mask); // lane = pair again
             __syncwarp();
         }
         __syncthreads();
@@ -1214,7 +1233,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
 #ifdef DAISY_FF_STATS
     {
-        unsigned long long h[32];
+        unsigned long long h[48];
         cudaMemcpyFromSymbol(h, g_ffstats, sizeof(h));
         const char *nm[4] = { "simple(n_main=0)", "occluded", "visible", "partial" };
         for (int c = 0; c < 4; c++)
@@ -1222,6 +1241,8 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
         fprintf(stderr, "ffstats simple&fully-visible %llu ; slab iterations pass0 %llu pass1 %llu\n", h[12], h[16], h[17]);
         fprintf(stderr, "ffstats faces: %d grids, face entries over all pairs %llu, pairs with neither list nor face %llu, cell lookups %llu, explicit tests in cells %llu, flat-ray tests in cells %llu, rays searching a face %llu\n",
                 ctx->nfaces, h[13], h[18], h[15], h[14], h[23], h[19]);
+        fprintf(stderr, "ffstats steep lookups: empty %llu, blocked by a covered cell %llu, explicit: own plane %llu, mixed cell %llu, covered but near an end point %llu; flat stretches: own plane %llu, other %llu\n",
+                h[38], h[37], h[32], h[33], h[34], h[35], h[36]);
         fprintf(stderr, "ffstats flush: rounds executed %llu, rounds if balanced over lanes %llu, tests queued %llu (%.1f lanes per executed round)\n",
                 h[22], h[20], h[21], h[22] ? (double)h[21] / h[22] : 0.0);
         {
@@ -1230,7 +1251,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
             for (int i = 0; i < 7; i++) tot += h[24 + i];
             for (int i = 0; i < 7; i++) fprintf(stderr, "ffstats warp-cycles %-18s %6.2f %%\n", ph[i], tot ? 100.0 * (double)h[24 + i] / (double)tot : 0.0);
         }
-        unsigned long long z[32] = { 0 };
+        unsigned long long z[48] = { 0 };
         cudaMemcpyToSymbol(g_ffstats, z, sizeof(z));
     }
 #endif

@@ -58,6 +58,12 @@ int daisy_ctx_set_samples(daisy_ctx *ctx, const float *uv, int S);
  * triangle t and at least one other triangle (exact for axis-aligned planes, fitted in double precision within 3e-7 x scene
  * extent otherwise), 0 = none.  The form-factor kernel skips triangles lying in the plane of a pair's own two patches. */
 int daisy_plane_ids(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int32_t *pid_out);
+/* diagnostic, host only: the planar face grids daisy_ctx_create builds (csrc/faces.cu) -- planes holding >= 32 triangles, at
+ * most 64 of them, each with a uniform 2-D grid whose cells are empty / covered / mixed and list the triangles near them.  The
+ * form-factor kernel resolves a visibility ray against a whole face with one plane crossing and one cell lookup.
+ * stats6[6 f ..] = triangles, cells, empty, covered, mixed cells, list entries of face f (f < max_faces); pid_out (may be
+ * NULL) = the plane ids after renumbering (face f = id f + 1). */
+int daisy_face_grid_stats(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int max_faces, int64_t *stats6, int32_t *nfaces_out, int32_t *pid_out);
 /* multi-GPU (one process per GPU): this context builds and owns the row block `rank` of `nranks` equal blocks of
  * rows_per_rank = ceil(N/nranks) rounded up to a multiple of 256 when nranks > 1 (a 256-column TMA tile of the
  * residual never straddles two blocks), of 4 when nranks == 1 (default rank 0 of 1 = all rows).  Callers must not

@@ -41,6 +41,13 @@ for r in rows:
                 return 0
         ins.append((int(r[2], 16), cur_file, cur_line, iv(r[ie]), iv(r[te]), iv(r[ss]), func))
 ins.sort()
+# an instruction inlined from a header appears once per file section: keep one row per address, preferring formfactor.cu's
+uniq = {}
+for rec in ins:
+    a = rec[0]
+    if a not in uniq or (rec[1] == "formfactor.cu" and uniq[a][1] != "formfactor.cu"):
+        uniq[a] = rec
+ins = [uniq[a] for a in sorted(uniq)]
 tot = sum(i[3] for i in ins) or 1
 tots = sum(i[5] for i in ins) or 1
 agg = {}
