@@ -590,7 +590,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                         const int ia0 = max(0, (int)floorf(fminf(a0, a1))), ia1 = min(g.x - 1, (int)floorf(fmaxf(a0, a1)));
                         const int ib0 = max(0, (int)floorf(fminf(b0, b1))), ib1 = min(g.y - 1, (int)floorf(fmaxf(b0, b1)));
                         if (ia0 <= ia1 && ib0 <= ib1) {
-                            if ((ia1 - ia0) + (ib1 - ib0) <= 40) {
+                            if ((ia1 - ia0) + (ib1 - ib0) <= 1000) {
                                 // the cells under the stretch, column by column (the b-range of the stretch inside a column, widened
                                 // by a hundredth of a cell); a triangle tested a moment ago is not tested again
                                 const float da = a1 - a0, rda = (fabsf(da) > 1e-6f) ? __fdividef(b1 - b0, da) : 0.f;
