@@ -281,7 +281,8 @@ class OptixPrimeFunctionality:
         p, o, r, a, b = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double(), C.c_double()
         _lib.check(_lib.lib().daisy_formfactors_stats(self._ctx, C.byref(p), C.byref(o), C.byref(r), C.byref(a), C.byref(b)))
         return {"pairs_traced": p.value, "pairs_owned": o.value, "rays": r.value, "lbvh_ms": a.value, "ff_ms": b.value,
-                "pairs_fallback": int(_lib.lib().daisy_formfactors_pairs_fallback(self._ctx))}
+                "pairs_fallback": int(_lib.lib().daisy_formfactors_pairs_fallback(self._ctx)),
+                "faces": int(_lib.lib().daisy_ctx_face_count(self._ctx))}
 
 
 

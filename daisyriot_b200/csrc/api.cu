@@ -633,6 +633,7 @@ extern "C" int daisy_formfactors_row_digest(daisy_ctx *ctx, int row0, int nrows,
     return DAISY_OK;
 }
 
+extern "C" int daisy_ctx_face_count(daisy_ctx *ctx) { return ctx ? ctx->nfaces : -1; }
 extern "C" int64_t daisy_formfactors_pairs_fallback(daisy_ctx *ctx) { return ctx ? ctx->pairs_heavy : -1; }
 
 extern "C" int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *pairs_owned, int64_t *rays, double *lbvh_ms, double *ff_ms) {

@@ -121,6 +121,8 @@ int daisy_formfactors_row_digest(daisy_ctx *ctx, int row0, int nrows, uint32_t *
  * their lower patch index inside this context's row range (summing that over all ranks counts every pair of the
  * matrix once), rays cast (= pairs_traced * S), and device milliseconds of the LBVH build and of the fused
  * form-factor/visibility kernel */
+/* number of planar face grids this context built (csrc/faces.cu; 0 with DAISY_FF_FACES=0 or in a scene without large planar faces) */
+int daisy_ctx_face_count(daisy_ctx *ctx);
 int daisy_formfactors_stats(daisy_ctx *ctx, int64_t *pairs_traced, int64_t *pairs_owned, int64_t *rays, double *lbvh_ms,
                             double *ff_ms);
 

@@ -231,6 +231,43 @@ def test_plane_ids_host_side(fixture_scenes):
     assert counts.max() <= 512 and (pc == 0).sum() > 0
 
 
+def test_face_grids_host_side(fixture_scenes):
+    """daisy_face_grid_stats (host only): the planar face grids of csrc/faces.cu.  Every quad of the synthetic Cornell box is a
+    face; its cells split into empty (the apron), covered (the inside) and mixed (the outline) and only a thin band is mixed.
+    A hole in a face turns the cells around it mixed; T-junctions (an edge not shared by exactly two triangles) do the same."""
+    import ctypes as C
+    from daisyriot_b200 import scenes
+    L = _lib.lib()
+
+    def grids(sc):
+        v = np.ascontiguousarray(sc.vertices, np.float32)
+        t = np.ascontiguousarray(sc.tri, np.int32)
+        st = np.zeros((64, 6), np.int64)
+        nf = C.c_int(0)
+        pid = np.zeros(t.shape[0], np.int32)
+        _lib.check(L.daisy_face_grid_stats(_lib.fptr(v), v.shape[0], _lib.iptr(t), t.shape[0], 64, st.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nf), _lib.iptr(pid)))
+        return st[:nf.value], pid
+
+    sc = scenes.cornell_box(8192)
+    st, pid = grids(sc)
+    assert st.shape[0] == 16 and (st[:, 0] == 512).all()
+    assert sorted(set(pid.tolist())) == list(range(1, 17))          # face f carries plane id f + 1
+    assert (st[:, 2] + st[:, 3] + st[:, 4] == st[:, 1]).all()        # empty + covered + mixed = cells
+    assert (st[:, 3] > 10 * st[:, 4]).all() and (st[:, 4] > 0).all()  # a thin mixed band around a covered inside
+    assert (st[:, 5] >= st[:, 3] + st[:, 4]).all()                   # every non-empty cell lists at least one triangle
+    # remove a block of 4 x 4 cells from the floor (quad 0): the hole's rim becomes mixed, its inside empty
+    keep = np.ones(sc.numtriangles, bool)
+    for j in range(6, 10):
+        keep[(j * 16 + 6) * 2:(j * 16 + 10) * 2] = False
+    sc2 = scenes.Scene(sc.vertices, sc.normals, sc.tri[keep], sc.mat_idx[keep], sc.materials, "holed")
+    st2, _ = grids(sc2)
+    f0 = int(np.argmin(st2[:, 0]))                                   # the face that lost 32 triangles
+    assert st2[f0, 0] == 512 - 32 and st2[f0, 4] > st[0, 4] and st2[f0, 2] > st[0, 2]
+    # curved geometry has no faces to speak of; the box around the balls does
+    stc, _ = grids(fixture_scenes["colorballs"])
+    assert 1 <= stc.shape[0] <= 64
+
+
 def test_committed_row_digests_cover_the_bench_workloads():
     import bench
     for name, (N, K, _) in bench.WORKLOADS.items():

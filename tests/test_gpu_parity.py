@@ -538,6 +538,87 @@ def test_irregular_walls_vs_bruteforce(dz, uv50, seed):
     p.close()
 
 
+@pytest.mark.parametrize("seed", [1, 2])
+def test_perforated_faces_vs_bruteforce(dz, uv50, seed):
+    """Adversarial input for the planar face grids (csrc/faces.cu): between a floor and a ceiling hangs a tilted plate with
+    holes, a ragged outline, T-junctions (cells cut in four next to uncut neighbours) and a second, overlapping sheet in the
+    very same plane; a fin stands ON the floor (its lower edge lies in the floor's plane, so rays leave and reach it flatly
+    and skim the floor); the sample pattern holds samples exactly on triangle edges and vertices.  Everything is rotated
+    arbitrarily.  Covered / mixed / empty cells, flat stretches and end-point margins all come into play; masks and matrix
+    must equal the brute-force oracle (every ray against every triangle) bit for bit."""
+    from daisyriot_b200.scenes import Scene
+    rng = np.random.RandomState(100 + seed)
+
+    def rot(axis, ang):
+        axis = axis / np.linalg.norm(axis)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+    R = rot(rng.normal(size=3), rng.uniform(0, 3)) if seed == 2 else np.eye(3)
+    V, T, VN = [], [], []
+
+    def sheet(origin, eu, ev, n, nu, nv, flip, keep=None, split=None):
+        """nu x nv cells; keep(i, j) False = hole; split(i, j) True = the cell is cut into four sub-cells (T-junctions)."""
+        ni = len(VN)
+        VN.append(n)
+
+        def vid(s, t):
+            V.append(origin + s * eu + t * ev)
+            return len(V) - 1
+
+        grid = [[vid(i / nu, j / nv) for i in range(nu + 1)] for j in range(nv + 1)]
+
+        def quad(a, b, c, d):  # a b / c d
+            tris = [(a, b, d), (a, d, c)] if rng.uniform() < 0.5 else [(a, b, c), (b, d, c)]
+            for t in tris:
+                T.append([*(t[::-1] if flip else t), ni, ni, ni])
+
+        for j in range(nv):
+            for i in range(nu):
+                if keep is not None and not keep(i, j):
+                    continue
+                a, b, c, d = grid[j][i], grid[j][i + 1], grid[j + 1][i], grid[j + 1][i + 1]
+                if split is not None and split(i, j):
+                    m = [[a, vid((i + .5) / nu, j / nv), b], [vid(i / nu, (j + .5) / nv), vid((i + .5) / nu, (j + .5) / nv), vid((i + 1) / nu, (j + .5) / nv)],
+                         [c, vid((i + .5) / nu, (j + 1) / nv), d]]
+                    for jj in range(2):
+                        for ii in range(2):
+                            quad(m[jj][ii], m[jj][ii + 1], m[jj + 1][ii], m[jj + 1][ii + 1])
+                else:
+                    quad(a, b, c, d)
+
+    ex, ey, ez = np.eye(3)
+    sheet(np.zeros(3), 6 * ex, 6 * ez, ey, 7, 6, True)                       # floor, facing +y
+    sheet(np.array([0, 4.0, 0]), 6 * ex, 6 * ez, -ey, 6, 7, False)           # ceiling, facing -y
+    holes = rng.uniform(size=(9, 9)) < 0.25
+    splits = rng.uniform(size=(9, 9)) < 0.2
+    pu, pv = 4.2 * ex + 0.5 * ey, 4.0 * ez + 0.3 * ey
+    pn = np.cross(pu, pv) / np.linalg.norm(np.cross(pu, pv))
+    sheet(np.array([0.8, 1.8, 0.9]), pu, pv, pn, 9, 9, False, keep=lambda i, j: not holes[j, i] and not (i > 5 and j > 6), split=lambda i, j: splits[j, i])
+    # a second sheet in the same plane, overlapping part of the first (its vertices are points of the first sheet's plane)
+    sheet(np.array([0.8, 1.8, 0.9]) + 0.31 * pu + 0.27 * pv, 0.45 * pu, 0.4 * pv, pn, 4, 4, False)
+    # a fin standing on the floor: its lower edge lies in the floor's plane
+    sheet(np.array([1.0, 0.0, 5.2]), 4.0 * ex + 0.3 * ez, 0.9 * ey, np.cross(4.0 * ex + 0.3 * ez, 0.9 * ey) / np.linalg.norm(np.cross(4.0 * ex + 0.3 * ez, 0.9 * ey)), 8, 2, False)
+    V = (np.asarray(V) @ R.T).astype(np.float32)
+    VN = (np.asarray(VN) @ R.T).astype(np.float32)
+    T = np.asarray(T, np.int32)
+    mats = [{"name": "w", "Kd": np.ones(3, np.float32), "Ke": np.zeros(3, np.float32), "Ks": np.zeros(3, np.float32)}]
+    sc = Scene(V, VN, T, np.zeros(len(T), np.int32), mats, f"perforated{seed}")
+    # the usual pattern with eight samples moved onto edges and vertices
+    uv = uv50.copy()
+    uv[:8] = np.array([[0, 0], [1, 0], [0, 1], [0.5, 0], [0, 0.5], [0.5, 0.5], [0.25, 0.75], [1e-4, 0.3]], np.float32)
+    p = _ctx(dz, sc, uv)
+    assert p.stats().get("faces", 1) >= 1
+    F = p.cudaCalculateRadiosityMatrix().rows()
+    masks = p.visibilityMasks()
+    F_ref, masks_ref, _ = _oracle(sc).radmat_rows(uv, 0, sc.numtriangles, brute=True)
+    vis = np.array([bin(int(m)).count("1") for m in masks_ref.ravel()])
+    assert (vis >= 40).sum() > 1000 and ((vis > 0) & (vis < 40)).sum() > 1000  # open and partially hidden pairs both occur
+    assert np.array_equal(masks, masks_ref)
+    assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
+    p.close()
+
+
 def test_per_pair_debug_entry_points_vs_oracle(dz, cornell512, uv50):
     """p2pFormfactorNusselt / p2pFormfactor / shootPatchRay (OptixPrimeFunctionality.cpp:273-306, :133-167, :456-469): host
     arithmetic around the GPU closest-hit query, against the same arithmetic around the oracle's closest hit."""
