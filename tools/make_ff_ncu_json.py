@@ -17,7 +17,7 @@ for path in sorted(glob.glob("gpurun_out/ffncu_*.csv")):
     f = lambda k: float(m[k]) if k in m and m[k] not in ("", "n/a") else None
     out[name] = {
         "kernel": "k_ff_tiles<0>", "workload": name,
-        "source": "ncu --metrics ... --clock-control none -k regex:k_ff_tiles -c 1 python tools/ff_build_only.py %s (round 2, final kernel; tools/ff_ncu_capture.sh)" % name,
+        "source": "ncu --metrics ... --clock-control none -k regex:k_ff_tiles -c 1 python tools/ff_build_only.py %s (round 2, face-grid kernel; tools/ff_ncu_capture.sh)" % name,
         "warp_instructions": f("smsp__inst_executed.sum"),
         "threads_active_per_warp_instruction": f("smsp__thread_inst_executed_per_inst_executed.ratio"),
         "issue_slots_active_pct": f("smsp__issue_active.avg.pct_of_peak_sustained_active"),
