@@ -98,6 +98,7 @@ SYMBOLS = {
     "daisy_solver_exchange_info": (_i, [_vp, C.POINTER(_vp), _i64p, _i64p]),
     "daisy_solver_step_finish": (_i, [_vp, _dp]),
     "daisy_solver_last_step_ms": (_i, [_vp, _dp]),
+    "daisy_solver_set_chained": (_i, [_vp, _i]),
 }
 
 _LIB = None

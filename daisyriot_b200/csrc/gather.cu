@@ -72,6 +72,8 @@ struct daisy_solver {
     bool sums_valid = true;
     std::vector<double> e_sums; // band sums of the emission
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool events_recorded = false;       // e0 / e1 bracket the most recent pass
+    bool chained = false;               // daisy_solver_set_chained: passes launched back to back without per-pass events
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -355,9 +357,15 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch (chained passes, launch_pass_K): the next pass's grid may be scheduled onto SMs as this one
+    // leaves them.  Its producer starts streaming F -- which no pass ever writes -- and only then waits for this grid to
+    // complete before touching the residual; everything else in the kernel is downstream of the producer's loads, and the
+    // other warps wait as well before they read or write global memory.  Without the launch attribute both are no-ops.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     uint32_t it = 0; // global step counter: stage = it % NST, phase = (it / NST) & 1
     int cursor = 0;
     Piece pc;
+    if (warp != NCW) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp > NCW) {
         // ------------------------------- epilogue warps (64 threads) -------------------------------
         // They take over each finished item from the consumers (named barriers 2/3: "item done", 4/5: "buffer free"), so
@@ -489,15 +497,29 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
         // single block's tail beyond n is zero-filled by the TMA unit)
         if (lane == 0) {
             unsigned ready = (E.enabled && E.wait_seq != 0ull) ? 0u : 0xffffffffu; // ranks whose block of the previous pass is known to be here
+            // the F tiles of the first NST steps go out before the previous pass is known to be complete
+            uint32_t pre = 0;
+            {
+                int cur2 = 0;
+                Piece p2;
+                while (pre < (uint32_t)NST && next_piece<T_COLS>(P, blockIdx.x, gridDim.x, cur2, p2))
+                    for (int s = p2.s0; s < p2.s1 && pre < (uint32_t)NST; s++, pre++) {
+                        mbar_expect_tx(&full[pre], (uint32_t)tma_stage_bytes<K>());
+                        tma_load_2d(stages + (size_t)pre * STAGE_F, &tmF, s * T_COLS, p2.rb * T_ROWS, &full[pre]);
+                    }
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             while (next_piece<T_COLS>(P, blockIdx.x, gridDim.x, cursor, pc)) {
                 const int row0 = pc.rb * T_ROWS;
                 for (int s = pc.s0; s < pc.s1; s++, it++) {
                     const int st = it % NST;
-                    mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
                     const int col0 = s * T_COLS;
                     float *sf = stages + (size_t)st * STAGE_F;
-                    mbar_expect_tx(&full[st], (uint32_t)tma_stage_bytes<K>());
-                    tma_load_2d(sf, &tmF, col0, row0, &full[st]);
+                    if (it >= pre) {
+                        mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
+                        mbar_expect_tx(&full[st], (uint32_t)tma_stage_bytes<K>());
+                        tma_load_2d(sf, &tmF, col0, row0, &full[st]);
+                    }
                     const int g = col0 / P.n, jl = col0 - g * P.n;
                     DZ_ASSERT(g >= 0 && g < 32 && col0 < P.ncols && row0 < P.nloc + T_ROWS);
                     if (!((ready >> g) & 1u)) {
@@ -785,7 +807,19 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
                 }
             }
         }
-        k_gather_tma<K><<<grid, (TmaCfg<K>::NCW + 3) * 32, smem, c->stream>>>(P, s->tmF, s->tmRes[s->cur], F);
+        {
+            // chained single-GPU passes: programmatic dependent launch lets this grid move onto SMs as the previous pass leaves
+            // them and stream its first F tiles meanwhile (the kernel waits for the previous grid before it touches anything
+            // a pass writes).  Multi-GPU passes keep plain stream order (their abort marker is read at kernel start).
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((TmaCfg<K>::NCW + 3) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = (s->fused_epi && s->chained && s->G == 1) ? 1 : 0;
+            DZ_CUDA(cudaLaunchKernelEx(&cfg, k_gather_tma<K>, P, s->tmF, s->tmRes[s->cur], F));
+        }
         DZ_CUDA(cudaGetLastError());
         if (s->fused_epi) return DAISY_OK; // the whole pass was that one launch
         rc = DAISY_OK;
@@ -1100,10 +1134,17 @@ extern "C" int daisy_solver_step_local(daisy_solver *s) {
     DzRange range_("gather pass");
     DZ_CUDA(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->stream;
-    DZ_CUDA(cudaEventRecord(s->e0, st));
+    if (!s->chained) DZ_CUDA(cudaEventRecord(s->e0, st)); // an event between two passes would keep them from overlapping
     int rc = launch_pass(s);
     if (rc) return rc;
-    DZ_CUDA(cudaEventRecord(s->e1, st));
+    if (!s->chained) DZ_CUDA(cudaEventRecord(s->e1, st));
+    s->events_recorded = !s->chained;
+    return DAISY_OK;
+}
+
+extern "C" int daisy_solver_set_chained(daisy_solver *s, int on) {
+    DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_set_chained: null solver");
+    s->chained = on != 0;
     return DAISY_OK;
 }
 
@@ -1135,7 +1176,10 @@ static int fetch_sums(daisy_solver *s) {
         return DAISY_E_STATE;
     }
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s->e0, s->e1) == cudaSuccess) s->last_ms = ms;
+    if (s->events_recorded) {
+        if (cudaEventElapsedTime(&ms, s->e0, s->e1) == cudaSuccess) s->last_ms = ms;
+        else cudaGetLastError(); // not an error of this call's work: do not leave it for the next cudaGetLastError()
+    }
     s->sums.assign(s->K, 0.0);
     for (int k = 0; k < s->K; k++) {
         double v = 0.0;
@@ -1290,6 +1334,7 @@ extern "C" int daisy_solver_step_fused(daisy_solver *s, double *band_sums) {
     int rc = launch_pass(s, wait_seq);
     if (rc) return rc;
     DZ_CUDA(cudaEventRecord(s->e1, st));
+    s->events_recorded = true;
     return daisy_solver_step_finish(s, band_sums);
 }
 

@@ -173,6 +173,11 @@ int daisy_solver_exchange_info(daisy_solver *s, void **d_next_buffer, int64_t *b
 int daisy_solver_step_finish(daisy_solver *s, double *band_sums);
 /* timing of the last step: device milliseconds of the gather kernel (CUDA events on the context's stream) */
 int daisy_solver_last_step_ms(daisy_solver *s, double *ms);
+/* on != 0: passes issued without reading the band sums (daisy_solver_step(s, NULL), daisy_solver_step_local) are chained --
+ * no per-pass events (daisy_solver_last_step_ms keeps its last value) and, on one GPU, programmatic dependent launch: the
+ * next pass's grid moves onto SMs as the previous pass leaves them and streams its first F tiles meanwhile.  Results are
+ * unchanged (the kernel waits for the previous pass before it reads or writes anything a pass writes). */
+int daisy_solver_set_chained(daisy_solver *s, int on);
 /* kernels one pass launches in this solver's configuration: 1 for K <= 9 (streaming, epilogue and exchange wait in one kernel) */
 int daisy_solver_launches_per_pass(daisy_solver *s);
 

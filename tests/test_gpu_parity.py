@@ -199,6 +199,40 @@ def test_gather_pass_vs_oracle(dz, cornell2048, uv50, K):
     p.close()
 
 
+@pytest.mark.parametrize("K", [3, 9])
+def test_chained_passes_change_nothing(dz, cornell2048, uv50, K):
+    """daisy_solver_set_chained: passes issued back to back without reading the band sums overlap (programmatic dependent
+    launch: the next pass streams its first F tiles while the previous one finishes).  Twelve chained passes must leave exactly
+    the B, residual and band sums that twelve passes with a host synchronisation after each one leave."""
+    from daisyriot_b200 import _lib
+    sc = cornell2048
+    p = _ctx(dz, sc, uv50)
+    p.cudaCalculateRadiosityMatrix()
+    rng = np.random.RandomState(40 + K)
+    M = rng.uniform(0, 0.3, (len(sc.materials), K, K)).astype(np.float32)
+    E = np.zeros((K, sc.numtriangles), np.float32)
+    E[:, sc.mat_idx == 0] = 5.0
+    L = _lib.lib()
+    got = {}
+    for chained in (0, 1):
+        s = _solver(dz, p, K, E, M, sc.mat_idx)
+        _lib.check(L.daisy_solver_set_chained(s, chained))
+        sums = np.zeros(K)
+        for it in range(12):
+            if chained:
+                _lib.check(L.daisy_solver_step(s, None))
+            else:
+                _lib.check(L.daisy_solver_step(s, sums.ctypes.data_as(C.POINTER(C.c_double))))
+        _lib.check(L.daisy_solver_band_sums(s, sums.ctypes.data_as(C.POINTER(C.c_double))))
+        B, R = np.empty_like(E), np.empty_like(E)
+        _lib.check(L.daisy_solver_read(s, _lib.fptr(B), _lib.fptr(R)))
+        got[chained] = (B, R, sums.copy())
+        L.daisy_solver_destroy(s)
+    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1]) and np.array_equal(got[0][2], got[1][2])
+    assert got[0][2].sum() > 0
+    p.close()
+
+
 def test_lightning_classes_match_oracle_loop(dz, cornell2048, uv50, coeff_model):
     """Spectral / RGB / BW flavours end to end on a built matrix: same pass count under the reference's stop rule and
     converged radiosity within 1e-5 of the FP64-accumulating oracle iteration."""
