@@ -72,6 +72,7 @@ struct daisy_solver {
     bool sums_valid = true;
     std::vector<double> e_sums; // band sums of the emission
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int pin16 = 0;                      // sixteenths of the local F rows kept in L2 across passes (plan())
     bool events_recorded = false;       // e0 / e1 bracket the most recent pass
     bool chained = false;               // daisy_solver_set_chained: passes launched back to back without per-pass events
 };
@@ -101,6 +102,11 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): evict_last keeps a tile in the 126 MB L2 from one pass to the next
+__device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
@@ -127,6 +133,10 @@ struct GatherParams {
     // gets the same number of steps whatever the matrix shape, and a row block is shared by at most a few CTAs ("pieces")
     int sk;                 // 1: stream-K pieces, 0: (row block, column split) items
     int sk_S, sk_L, sk_total; // steps per row block, steps per CTA, steps in total
+    // L2 residency: the F tiles whose step number s has (s * 11 + rb * 5) % 16 < pin16 are loaded evict_last, the others
+    // evict_first -- a fixed subset of the matrix, spread evenly over the CTAs, that stays in L2 from pass to pass when the
+    // matrix is not much larger than L2 (the reference's own scenes: 164 / 238 MB against 126 MB of L2)
+    int pin16;
 };
 
 // one unit of work of k_gather_tma: steps [s0, s1) of row block rb; idx / np = this piece's ordinal among / number of the
@@ -497,6 +507,10 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
         // single block's tail beyond n is zero-filled by the TMA unit)
         if (lane == 0) {
             unsigned ready = (E.enabled && E.wait_seq != 0ull) ? 0u : 0xffffffffu; // ranks whose block of the previous pass is known to be here
+            uint64_t pol_last, pol_first;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+            auto pol = [&](int rb, int s) -> uint64_t { return (((s * 11 + rb * 5) & 15) < P.pin16) ? pol_last : pol_first; };
             // the F tiles of the first NST steps go out before the previous pass is known to be complete
             uint32_t pre = 0;
             {
@@ -505,7 +519,7 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                 while (pre < (uint32_t)NST && next_piece<T_COLS>(P, blockIdx.x, gridDim.x, cur2, p2))
                     for (int s = p2.s0; s < p2.s1 && pre < (uint32_t)NST; s++, pre++) {
                         mbar_expect_tx(&full[pre], (uint32_t)tma_stage_bytes<K>());
-                        tma_load_2d(stages + (size_t)pre * STAGE_F, &tmF, s * T_COLS, p2.rb * T_ROWS, &full[pre]);
+                        tma_load_2d_hint(stages + (size_t)pre * STAGE_F, &tmF, s * T_COLS, p2.rb * T_ROWS, &full[pre], pol(p2.rb, s));
                     }
             }
             asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -518,7 +532,7 @@ k_gather_tma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                     if (it >= pre) {
                         mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
                         mbar_expect_tx(&full[st], (uint32_t)tma_stage_bytes<K>());
-                        tma_load_2d(sf, &tmF, col0, row0, &full[st]);
+                        tma_load_2d_hint(sf, &tmF, col0, row0, &full[st], pol(pc.rb, s));
                     }
                     const int g = col0 / P.n, jl = col0 - g * P.n;
                     DZ_ASSERT(g >= 0 && g < 32 && col0 < P.ncols && row0 < P.nloc + T_ROWS);
@@ -759,7 +773,7 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
     P.F = c->d_F; P.ldF = c->ldF; P.nloc = s->nloc; P.ncols = s->G * s->n; P.n = s->n;
     P.res = s->d_res[s->cur]; P.bstride = s->bstride; P.partial = s->d_partial;
     P.nsplit = s->nsplit; P.colw = s->colw; P.nrb = (s->nloc + G_WARPS * s->R - 1) / (G_WARPS * s->R);
-    P.sk = 0; P.sk_S = P.sk_L = P.sk_total = 0;
+    P.sk = 0; P.sk_S = P.sk_L = P.sk_total = 0; P.pin16 = 0;
     int rc;
     if (s->use_mma && (K == 16 || K == 32)) {
         if constexpr (K == 16 || K == 32) {
@@ -786,6 +800,7 @@ static int launch_pass_K(daisy_solver *s, unsigned long long wait_seq) {
         }
         P.nrb = (s->nloc + tma_rows<K>() - 1) / tma_rows<K>();
         P.sk = s->fused_epi ? 1 : 0; P.sk_S = s->sk_S; P.sk_L = s->sk_L; P.sk_total = s->sk_total;
+        P.pin16 = s->pin16;
         const int grid = s->fused_epi ? s->sk_grid : s->grid;
         FusedEpi F;
         memset(&F, 0, sizeof(F));
@@ -973,6 +988,21 @@ static void plan(daisy_solver *s) {
         s->sk_L = (s->sk_total + s->sk_grid - 1) / s->sk_grid;
         if (s->sk_L < 1) s->sk_L = 1;
         s->sk_maxp = s->sk_S / s->sk_L + 2;
+        // L2 residency (GatherParams::pin16): keep ~45 % of the L2 filled with F tiles that are read again next pass; the rest
+        // of the matrix streams through evict_first (which by itself is worth 9 % on the 164 MB matrix: the stream no longer
+        // pushes the residual vectors out).  Measured on the reference's scenes (164 / 238 MB): best at 61 / 45 MB pinned, worse
+        // from ~70 MB on (the two L2 halves mirror lines read from both dies).  DAISY_GATHER_PIN16 = 0..16 overrides.
+        {
+            int l2 = 0;
+            cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, s->ctx->device);
+            const double fbytes = (double)s->nloc * (double)ncols * 4.0;
+            int p16 = fbytes > 0.0 ? (int)floor(16.0 * 0.45 * (double)l2 / fbytes) : 0;
+            if (p16 > 16) p16 = 16;
+            if (p16 < 0) p16 = 0;
+            const char *e3 = getenv("DAISY_GATHER_PIN16");
+            if (e3) { p16 = atoi(e3); if (p16 < 0) p16 = 0; if (p16 > 16) p16 = 16; }
+            s->pin16 = p16;
+        }
     }
 }
 
