@@ -328,6 +328,7 @@ def parity_block(optixP, solver, sc, uv, E, M, K, world, rank, torch, name, stop
             if not (host_sums.sum() > stop_threshold):
                 host_done = True
         band_max = np.abs(res_new).max(1).astype(np.float64) + 1e-300
+        band_max_B = np.abs(Bl).max(1).astype(np.float64) + 1e-300
         for i in mine:
             r = int(rows[i])
             want = Mr[i].T @ (res_prev.astype(np.float64) @ F_ref[i].astype(np.float64))   # M_p (F[r,:] . residual_k)_k
@@ -337,7 +338,7 @@ def parity_block(optixP, solver, sc, uv, E, M, K, world, rank, torch, name, stop
             if big.any():
                 max_rel_res = max(max_rel_res, float((np.abs(got - want)[big] / np.abs(want)[big]).max()))
             gotB = Bl[:, r - r0].astype(np.float64)
-            bigB = np.abs(Bchk[i]) > 0
+            bigB = np.abs(Bchk[i]) > FLOOR * band_max_B  # same floor as for the residual: FP64 keeps values FP32 flushes to zero
             if bigB.any():
                 max_rel_B = max(max_rel_B, float((np.abs(gotB - Bchk[i])[bigB] / np.abs(Bchk[i])[bigB]).max()))
         res_prev = res_new
