@@ -180,6 +180,41 @@ __device__ __forceinline__ bool wray_tri_sel(const WRay &w, f3 va, f3 vb, f3 vc,
     return true;
 }
 
+// The same test for callers that only want the distance (the visibility rays of the form-factor kernel): identical
+// operations up to T and det; when their signs already say t <= 0 the IEEE division is skipped (T/det would be negative or a
+// signed zero, both rejected), otherwise t is the very same quotient.
+__device__ __forceinline__ bool wray_tri_t(const WRay &w, f3 va, f3 vb, f3 vc, float &t) {
+    f3 A = e_sub(va, w.o), B = e_sub(vb, w.o), C = e_sub(vc, w.o);
+    const bool r0 = w.perm & 1, r1 = w.perm & 2, sw = w.perm & 4;
+    const float A0 = r0 ? A.y : (r1 ? A.z : A.x), A1 = r0 ? A.z : (r1 ? A.x : A.y), Akz = r0 ? A.x : (r1 ? A.y : A.z);
+    const float B0 = r0 ? B.y : (r1 ? B.z : B.x), B1 = r0 ? B.z : (r1 ? B.x : B.y), Bkz = r0 ? B.x : (r1 ? B.y : B.z);
+    const float C0 = r0 ? C.y : (r1 ? C.z : C.x), C1 = r0 ? C.z : (r1 ? C.x : C.y), Ckz = r0 ? C.x : (r1 ? C.y : C.z);
+    const float Akx = sw ? A1 : A0, Aky = sw ? A0 : A1;
+    const float Bkx = sw ? B1 : B0, Bky = sw ? B0 : B1;
+    const float Ckx = sw ? C1 : C0, Cky = sw ? C0 : C1;
+    float Ax = fs(Akx, fm(w.Sx, Akz)), Ay = fs(Aky, fm(w.Sy, Akz));
+    float Bx = fs(Bkx, fm(w.Sx, Bkz)), By = fs(Bky, fm(w.Sy, Bkz));
+    float Cx = fs(Ckx, fm(w.Sx, Ckz)), Cy = fs(Cky, fm(w.Sy, Ckz));
+    float U = fs(fm(Cx, By), fm(Cy, Bx));
+    float V = fs(fm(Ax, Cy), fm(Ay, Cx));
+    float W = fs(fm(Bx, Ay), fm(By, Ax));
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        U = __double2float_rn(__dsub_rn(__dmul_rn((double)Cx, (double)By), __dmul_rn((double)Cy, (double)Bx)));
+        V = __double2float_rn(__dsub_rn(__dmul_rn((double)Ax, (double)Cy), __dmul_rn((double)Ay, (double)Cx)));
+        W = __double2float_rn(__dsub_rn(__dmul_rn((double)Bx, (double)Ay), __dmul_rn((double)By, (double)Ax)));
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+    float det = fa(fa(U, V), W);
+    if (det == 0.0f) return false;
+    float Az = fm(w.Sz, Akz), Bz = fm(w.Sz, Bkz), Cz = fm(w.Sz, Ckz);
+    float T = fa(fa(fm(U, Az), fm(V, Bz)), fm(W, Cz));
+    if (T == 0.0f || ((T < 0.0f) != (det < 0.0f))) return false;
+    float tt = fd(T, det);
+    if (!(tt > 0.0f) || isinf(tt)) return false;
+    t = tt;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // BVH node (64 B): both child boxes live in the parent, so one node fetch decides both descents.
 // child < 0 => leaf holding triangle ~child.

@@ -298,11 +298,11 @@ __device__ __noinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const T
     f3 dir = e_normalize(e_sub(dst, org));      // optix::normalize(dest - origin)
     f3 o = e_add(org, e_scale(dir, 0.000001f)); // origin + normalize(dest - origin)*0.000001f
     WRay w = wray_setup(o, dir);
-    float thi, uu, vv;
-    if (!wray_tri_sel(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv)) return false;
+    float thi;
+    if (!wray_tri_t(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi)) return false;
     float tk;
     // the origin patch itself takes part like any other triangle (lo < hi, so a tie on t hides hi)
-    if (wray_tri_sel(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) return false;
+    if (wray_tri_t(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk) && tk <= thi) return false;
     f3 inv = mk3(1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z);
     int stack[64];
     int sp = 0;
@@ -312,7 +312,7 @@ __device__ __noinline__ bool ray_sees(const BvhNode *__restrict__ nodes, const T
             int k = ~cur;
             if (k != lo && k != hi) {
                 TriVerts t = tv[k];
-                if (wray_tri_sel(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return false;
+                if (wray_tri_t(w, xyz(t.a), xyz(t.b), xyz(t.c), tk) && (tk < thi || (tk == thi && k < hi))) return false;
             }
             if (sp == 0) break;
             cur = stack[--sp];
@@ -499,14 +499,14 @@ __device__ __noinline__ bool face_blocks_ray(const BvhNode *__restrict__ nodes, 
     if (cur < 0) return false;
     while (true) {
         const BvhNode nd = nodes[cur];
-        float tl, tr, tk, uu, vv;
+        float tl, tr, tk;
         bool hl = (nd.d.z <= 0 || nd.d.z == fpid) && ray_box(o, inv, nd.a.x, nd.a.y, nd.a.z, nd.a.w, nd.b.x, nd.b.y, thi, tl);
         bool hr = (nd.d.w <= 0 || nd.d.w == fpid) && ray_box(o, inv, nd.b.z, nd.b.w, nd.c.x, nd.c.y, nd.c.z, nd.c.w, thi, tr);
         if (hl && nd.d.x < 0) {
             const int k = ~nd.d.x;
             if (nd.d.z == fpid && k != lo && k != hi) {
                 const TriVerts t = tv[k];
-                if (wray_tri_sel(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return true;
+                if (wray_tri_t(w, xyz(t.a), xyz(t.b), xyz(t.c), tk) && (tk < thi || (tk == thi && k < hi))) return true;
             }
             hl = false;
         }
@@ -514,7 +514,7 @@ __device__ __noinline__ bool face_blocks_ray(const BvhNode *__restrict__ nodes, 
             const int k = ~nd.d.y;
             if (nd.d.w == fpid && k != lo && k != hi) {
                 const TriVerts t = tv[k];
-                if (wray_tri_sel(w, xyz(t.a), xyz(t.b), xyz(t.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) return true;
+                if (wray_tri_t(w, xyz(t.a), xyz(t.b), xyz(t.c), tk) && (tk < thi || (tk == thi && k < hi))) return true;
             }
             hr = false;
         }
@@ -543,9 +543,9 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         f3 dir = e_normalize(e_sub(dst, org));
         f3 o = e_add(org, e_scale(dir, 0.000001f));
         WRay w = wray_setup(o, dir);
-        float thi = 0.f, uu, vv, tk;
-        bool alive = (i < S) && wray_tri_sel(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi, uu, vv);
-        if (alive && wray_tri_sel(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk, uu, vv) && tk <= thi) alive = false;
+        float thi = 0.f, tk;
+        bool alive = (i < S) && wray_tri_t(w, xyz(Thi.a), xyz(Thi.b), xyz(Thi.c), thi);
+        if (alive && wray_tri_t(w, xyz(Tlo.a), xyz(Tlo.b), xyz(Tlo.c), tk) && tk <= thi) alive = false;
         // Face grids first: one plane crossing and one cell lookup per (ray, face).  A covered cell crossed safely between the
         // ray's end points blocks the ray (some triangle of the face accepts it, faces.cu); an empty cell or a crossing beyond
         // the end points cannot; everything else runs the watertight test on the cell's own short list.
@@ -615,7 +615,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                                             atomicAdd(&g_ffstats[23], 1ull);
 #endif
                                             const TriVerts tr = tv[k];
-                                            if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) { alive = false; break; }
+                                            if (wray_tri_t(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk) && (tk < thi || (tk == thi && k < hi))) { alive = false; break; }
                                         }
                                     }
                                 }
@@ -658,7 +658,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                                     atomicAdd(&g_ffstats[14], 1ull);
 #endif
                                     const TriVerts tr = tv[k];
-                                    if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) { alive = false; break; }
+                                    if (wray_tri_t(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk) && (tk < thi || (tk == thi && k < hi))) { alive = false; break; }
                                 }
                             }
                         }
@@ -670,12 +670,12 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
         // neighbour lists are needed by the samples closer to an edge than the pair's required margin (see below)
         unsigned edge = 0;
         if ((nbr_lo || nbr_hi) && pass * 32 + 31 >= n_inner) edge = __ballot_sync(0xffffffffu, alive && i >= n_inner && mg < m_req);
-        // reciprocal direction (only the slab tests of the candidate list and of the neighbour lists use it), kept finite: with
+        // reciprocal direction (only the slab tests of the candidate list use it), kept finite: with
         // inv = inf the pre-multiplied form would turn a box that straddles 0 on an axis the ray is parallel to into (-inf, NaN)
         // and reject it
         f3 inv = mk3(0.f, 0.f, 0.f), oi = inv;
         bool neg_x = false, neg_y = false, neg_z = false, sorted = false;
-        if (n_main > 0 || edge) {
+        if (n_main > 0) {
             inv = mk3(1.0f / (fabsf(dir.x) > 1e-30f ? dir.x : copysignf(1e-30f, dir.x)), 1.0f / (fabsf(dir.y) > 1e-30f ? dir.y : copysignf(1e-30f, dir.y)),
                       1.0f / (fabsf(dir.z) > 1e-30f ? dir.z : copysignf(1e-30f, dir.z)));
             oi = mk3(o.x * inv.x, o.y * inv.y, o.z * inv.z);
@@ -707,7 +707,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                     const int k = wk[(qreg >> (4 * t)) & 15];
                     DZ_ASSERT(k >= 0 && qlen <= FF_QCAP);
                     TriVerts tr = tv[k];
-                    if (wray_tri_sel(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk, uu, vv) && (tk < thi || (tk == thi && k < hi))) alive = false;
+                    if (wray_tri_t(w, xyz(tr.a), xyz(tr.b), xyz(tr.c), tk) && (tk < thi || (tk == thi && k < hi))) alive = false;
                 }
             }
             qlen = 0;
@@ -776,14 +776,19 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                         we.o.x = __shfl_sync(0xffffffffu, w.o.x, e); we.o.y = __shfl_sync(0xffffffffu, w.o.y, e); we.o.z = __shfl_sync(0xffffffffu, w.o.z, e);
                         we.perm = __shfl_sync(0xffffffffu, w.perm, e); we.kx = we.ky = we.kz = 0; // the select-based test reads perm only
                         we.Sx = __shfl_sync(0xffffffffu, w.Sx, e); we.Sy = __shfl_sync(0xffffffffu, w.Sy, e); we.Sz = __shfl_sync(0xffffffffu, w.Sz, e);
-                        const f3 inve = mk3(__shfl_sync(0xffffffffu, inv.x, e), __shfl_sync(0xffffffffu, inv.y, e), __shfl_sync(0xffffffffu, inv.z, e));
-                        const f3 oie = mk3(__shfl_sync(0xffffffffu, oi.x, e), __shfl_sync(0xffffffffu, oi.y, e), __shfl_sync(0xffffffffu, oi.z, e));
+                        // reciprocal direction of the broadcast ray (a conservative box filter: the fast reciprocal's 2 ulp are far
+                        // inside the slab test's 1e-5 slack), kept finite as above
+                        const f3 dre = mk3(__shfl_sync(0xffffffffu, dir.x, e), __shfl_sync(0xffffffffu, dir.y, e), __shfl_sync(0xffffffffu, dir.z, e));
+                        const f3 inve = mk3(__fdividef(1.0f, fabsf(dre.x) > 1e-30f ? dre.x : copysignf(1e-30f, dre.x)),
+                                            __fdividef(1.0f, fabsf(dre.y) > 1e-30f ? dre.y : copysignf(1e-30f, dre.y)),
+                                            __fdividef(1.0f, fabsf(dre.z) > 1e-30f ? dre.z : copysignf(1e-30f, dre.z)));
+                        const f3 oie = mk3(we.o.x * inve.x, we.o.y * inve.y, we.o.z * inve.z);
                         const float thie = __shfl_sync(0xffffffffu, thi, e);
                         bool hit = false;
                         if (k >= 0 && ray_box_fma(oie, inve, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z, thie)) {
                             const TriVerts tr = tv[k];
-                            float t2, u2, v2;
-                            if (wray_tri_sel(we, xyz(tr.a), xyz(tr.b), xyz(tr.c), t2, u2, v2) && (t2 < thie || (t2 == thie && k < hi))) hit = true;
+                            float t2;
+                            if (wray_tri_t(we, xyz(tr.a), xyz(tr.b), xyz(tr.c), t2) && (t2 < thie || (t2 == thie && k < hi))) hit = true;
                         }
                         if (__any_sync(0xffffffffu, hit)) { if (lane == e) alive = false; edge &= ~(1u << e); }
                     }
