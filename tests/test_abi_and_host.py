@@ -272,7 +272,7 @@ def test_committed_row_digests_cover_the_bench_workloads():
     import bench
     for name, (N, K, _) in bench.WORKLOADS.items():
         path = os.path.join(GOLDEN, f"rowdigest_{name}.npz")
-        if name == "cornell_8k":
+        if name == "cornell_8k" or name in bench.SAME_MATRIX_AS:
             continue
         assert os.path.exists(path), path
         g = np.load(path)
