@@ -2,6 +2,7 @@
 // The solver half of the ABI lives in gather.cu.
 #include "daisy_common.cuh"
 #include <stdarg.h>
+#include <chrono>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -438,12 +439,17 @@ extern "C" int daisy_formfactors_build(daisy_ctx *ctx, int variant) {
     DZ_REQUIRE(ctx->S >= 1, DAISY_E_STATE, "daisy_formfactors_build: call daisy_ctx_set_samples first");
     DzRange range_("daisy_formfactors_build: fused form factors + visibility (k_ff_tiles)");
     DZ_CUDA(cudaSetDevice(ctx->device));
+    const bool timing = getenv("DAISY_TIMING") != nullptr; // stderr: where the wall time of the call goes
+    const auto t0 = std::chrono::steady_clock::now();
     int rc = ensure_F(ctx);
     if (rc) return rc;
+    if (timing) { cudaStreamSynchronize(ctx->stream); fprintf(stderr, "daisy_formfactors_build: matrix allocation + zero fill %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count()); }
     rc = dz_set_samples_const(ctx);
     if (rc) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     rc = dz_build_formfactors(ctx, variant, nullptr, 0, 0, true);
     if (rc) return rc;
+    if (timing) fprintf(stderr, "daisy_formfactors_build: tile list + kernel + clean-up %.3f s (kernel %.3f s)\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(), ctx->ff_ms * 1e-3);
     ctx->have_F = true;
     return DAISY_OK;
 }

@@ -1409,13 +1409,14 @@ extern "C" int daisy_solver_band_sums(daisy_solver *s, double *band_sums) {
 extern "C" int daisy_solver_read(daisy_solver *s, float *B, float *residual) {
     DZ_REQUIRE(s, DAISY_E_INVALID, "daisy_solver_read: null solver");
     DZ_CUDA(cudaSetDevice(s->ctx->device));
-    DZ_CUDA(cudaStreamSynchronize(s->ctx->stream));
-    // local rows only: out[k*nloc + pl]
+    // local rows only: out[k*nloc + pl]; both copies ride the solver's stream behind the passes, one synchronisation at the end
+    cudaStream_t st = s->ctx->stream;
     if (B)
-        DZ_CUDA(cudaMemcpy2D(B, sizeof(float) * s->nloc, s->d_B, sizeof(float) * s->n, sizeof(float) * s->nloc, s->K, cudaMemcpyDeviceToHost));
+        DZ_CUDA(cudaMemcpy2DAsync(B, sizeof(float) * s->nloc, s->d_B, sizeof(float) * s->n, sizeof(float) * s->nloc, s->K, cudaMemcpyDeviceToHost, st));
     if (residual)
-        DZ_CUDA(cudaMemcpy2D(residual, sizeof(float) * s->nloc, s->d_res[s->cur] + (size_t)s->rank * s->bstride, sizeof(float) * s->n,
-                             sizeof(float) * s->nloc, s->K, cudaMemcpyDeviceToHost));
+        DZ_CUDA(cudaMemcpy2DAsync(residual, sizeof(float) * s->nloc, s->d_res[s->cur] + (size_t)s->rank * s->bstride, sizeof(float) * s->n,
+                                  sizeof(float) * s->nloc, s->K, cudaMemcpyDeviceToHost, st));
+    DZ_CUDA(cudaStreamSynchronize(st));
     return DAISY_OK;
 }
 
