@@ -12,6 +12,7 @@
 // mirrored tiles coalesced through shared memory -- into this rank's matrix or a peer's over NVLink.
 #include "daisy_common.cuh"
 #include <math.h>
+#include <chrono>
 #include <stdlib.h>
 #include <vector>
 
@@ -1157,6 +1158,14 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     const int N = ctx->N;
     if (N == 0) return DAISY_OK;
     cudaStream_t st = ctx->stream;
+    const bool timing = getenv("DAISY_TIMING") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  dz_build_formfactors: %-28s %.3f s\n", what, std::chrono::duration<double>(now - tprev).count());
+        tprev = now;
+    };
     const int ntiles = (N + TILE - 1) / TILE;
     // row range of interest: the context's rows when writing F, else the mask rows
     int r0 = write_F ? ctx->row0 : mrow0, r1 = write_F ? ctx->row1 : mrow1;
@@ -1187,6 +1196,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     for (int R = 0; R < ntiles; R++)
         for (int C = R; C < ntiles; C++)
             if (mine(R, C)) h_jobs[k++] = make_int2(R, C);
+    lap("tile list (host)");
     int2 *d_jobs = nullptr;
     int *d_counter = nullptr;
     unsigned long long *d_pairs = nullptr;
@@ -1224,6 +1234,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     int *d_scratch = nullptr;
     DZ_CUDA(cudaMalloc(&d_scratch, sizeof(int) * (size_t)(grid > 0 ? grid : 1) * FF_THREADS * SHAFT_CAP));
     P.scratch = d_scratch;
+    lap("allocations, uploads");
     DZ_CUDA(cudaEventRecord(e0, st));
     if (grid > 0) {
         if (variant == DAISY_FF_DEVICE) k_ff_tiles<DAISY_FF_DEVICE><<<grid, FF_THREADS, smem, st>>>(P);
@@ -1236,6 +1247,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     DZ_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
     DZ_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    lap("kernel");
 #ifdef DAISY_FF_STATS
     {
         unsigned long long h[48];
@@ -1264,5 +1276,6 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_jobs); cudaFree(d_counter); cudaFree(d_pairs); cudaFree(d_scratch);
     free(h_jobs);
+    lap("clean-up");
     return DAISY_OK;
 }
