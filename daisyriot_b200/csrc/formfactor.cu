@@ -823,6 +823,7 @@ struct FFParams {
     const int *order;     // tile composition: slot -> triangle id (-1 = empty slot); tile T holds slots [64 T, 64 T + 64)
     int n_inner;          // samples [0, n_inner) of the device-order pattern are inner samples
     int ring_on;          // coplanar skipping enabled
+    int all_heavy;        // the sample pattern leaves the triangle: no culling of any kind, per-ray LBVH walks for every pair
     int *scratch;         // gridDim.x * FF_THREADS * SHAFT_CAP candidate slots
     int root, N, S;
     int row0, row1;      // rows this context owns
@@ -1032,8 +1033,10 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
                 // EDGE_MARGIN h cos >= 128 eps (distance) on the destination side.
                 bool on_lo = false, on_hi = false;
                 if (P.ring_on) pair_premise(A, B, sm.pl[ilo], sm.pl[ihi], on_lo, on_hi, m_req);
-                ncand = shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi], my_cand,
-                                         P.faces, P.nfaces, fmask);
+                // a sample pattern with points outside the triangle (no reference pattern has any): rays may leave the hull of the
+                // two patches, so nothing is culled -- every pair takes the per-ray LBVH walk of phase 2b
+                ncand = P.all_heavy ? -1 : shaft_candidates(P.nodes, P.root, sh, on_lo ? sm.pid[ilo] : 0, on_hi ? sm.pid[ihi] : 0, sm.id[ilo], sm.id[ihi],
+                                                            my_cand, P.faces, P.nfaces, fmask);
                 if (ncand >= 0) ncand |= (on_lo ? 0x10000 : 0) | (on_hi ? 0x20000 : 0);
                 if (ncand < 0) { // the lists do not fit: flag the pair, phase 2b walks the LBVH per ray
                     s_list[q] = (unsigned short)(idx | PAIR_HEAVY);
@@ -1213,6 +1216,12 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     P.faces = ctx->d_faces; P.face_cells = ctx->d_face_cells; P.face_lists = ctx->d_face_lists; P.nfaces = ctx->nfaces; P.face_tm = 4.0f * ctx->pad;
 
     { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
+    P.all_heavy = 0;
+    for (int i = 0; i < ctx->S; i++) {
+        const float u = ctx->h_uv[2 * i], v = ctx->h_uv[2 * i + 1];
+        if (!(u >= 0.f && v >= 0.f && u + v <= 1.0f + 1e-6f)) P.all_heavy = 1;
+    }
+    if (P.all_heavy) P.ring_on = 0;
     P.row0 = r0; P.row1 = r1;
     P.F = write_F ? ctx->d_F : nullptr; P.ldF = ctx->ldF;
     P.peer_mode = peer ? 1 : 0; P.n_per_rank = ctx->rows_per_rank;

@@ -54,6 +54,8 @@ void daisy_ctx_destroy(daisy_ctx *ctx);
 /* the `rands` pattern (VS/OptixPrimeFunctionality.cpp:55-63); uv = S x {u,v}, 1 <= S <= 64.  The reference
  * draws it from rand() seeded by wall-clock time, so the drop-in takes it as an input. */
 int daisy_ctx_set_samples(daisy_ctx *ctx, const float *uv, int S);
+/* (the reference's pattern has u >= 0, v >= 0, u + v <= 1; a pattern with points outside the triangle is accepted and gives the
+ * same closest-hit answers, but the form-factor kernel then culls nothing and walks the LBVH for every ray) */
 /* diagnostic, host only (no device needed): the plane ids daisy_ctx_create assigns -- pid_out[t] >= 1 names a plane shared by
  * triangle t and at least one other triangle (exact for axis-aligned planes, fitted in double precision within 3e-7 x scene
  * extent otherwise), 0 = none.  The form-factor kernel skips triangles lying in the plane of a pair's own two patches. */

@@ -572,6 +572,24 @@ def test_irregular_walls_vs_bruteforce(dz, uv50, seed):
     p.close()
 
 
+def test_samples_outside_the_triangle_vs_bruteforce(dz, cornell512):
+    """The reference's pattern keeps (u, v) inside the triangle (OptixPrimeFunctionality.cpp:55-63) and every culling step of
+    the kernel relies on it.  A caller's pattern that does not (u + v > 1, negative v) still has to give the closest-hit
+    answer: the kernel then culls nothing and walks the LBVH per ray."""
+    rng = np.random.RandomState(5)
+    uv = rng.uniform(-0.3, 1.2, (50, 2)).astype(np.float32)
+    assert ((uv.sum(1) > 1) | (uv.min(1) < 0)).sum() > 10
+    sc = cornell512
+    p = _ctx(dz, sc, uv)
+    F = p.cudaCalculateRadiosityMatrix().rows()
+    masks = p.visibilityMasks()
+    F_ref, masks_ref, _ = _oracle(sc).radmat_rows(uv, 0, sc.numtriangles, brute=True)
+    assert (masks_ref != 0).sum() > 1000
+    assert np.array_equal(masks, masks_ref)
+    assert np.array_equal(F.view(np.uint32), F_ref.view(np.uint32))
+    p.close()
+
+
 @pytest.mark.parametrize("seed", [1, 2])
 def test_perforated_faces_vs_bruteforce(dz, uv50, seed):
     """Adversarial input for the planar face grids (csrc/faces.cu): between a floor and a ceiling hangs a tilted plate with
