@@ -282,8 +282,13 @@ static int build_face_tables(float ext_f, float pad, const float *vertices, cons
     {
         std::atomic<size_t> next(0);
         auto worker = [&]() {
-            for (size_t i = next.fetch_add(1); i < order.size(); i = next.fetch_add(1))
-                build_one_face((double)ext_f, pad, vertices, tri_idx, members[(size_t)order[i]], built[i]);
+            for (size_t i = next.fetch_add(1); i < order.size(); i = next.fetch_add(1)) {
+                try {
+                    build_one_face((double)ext_f, pad, vertices, tri_idx, members[(size_t)order[i]], built[i]);
+                } catch (...) { // out of host memory for one face's tables: the face simply gets no grid
+                    built[i] = FaceBuild();
+                }
+            }
         };
         unsigned nthr = std::thread::hardware_concurrency();
         if (nthr == 0) nthr = 1;
