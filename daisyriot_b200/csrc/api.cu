@@ -26,8 +26,23 @@ extern "C" int daisy_device_count(void) {
     return n;
 }
 
+cudaError_t dz_scratch(daisy_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_bytes[slot] < bytes) {
+        cudaFree(ctx->scratch[slot]);
+        ctx->scratch[slot] = nullptr; ctx->scratch_bytes[slot] = 0;
+        const size_t want = bytes + bytes / 4; // some head room: frame sizes creep
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&ctx->scratch[slot], bytes); if (e != cudaSuccess) return e; ctx->scratch_bytes[slot] = bytes; }
+        else ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return cudaSuccess;
+}
+
 static void free_ctx(daisy_ctx *c) {
     if (!c) return;
+    for (int i = 0; i < 6; i++) cudaFree(c->scratch[i]);
     if (c->peers_set && c->peers_ipc)
         for (int g = 0; g < c->nranks && g < 16; g++)
             if (g != c->rank && c->peerF[g]) cudaIpcCloseMemHandle(c->peerF[g]);
@@ -386,15 +401,14 @@ extern "C" int daisy_query_closest(daisy_ctx *ctx, int n, const float *rays6, da
     DZ_CUDA(cudaSetDevice(ctx->device));
     float *d_r = nullptr;
     daisy_hit *d_h = nullptr;
-    DZ_CUDA(cudaMalloc(&d_r, sizeof(float) * 6 * (size_t)n));
-    cudaError_t e = cudaMalloc(&d_h, sizeof(daisy_hit) * (size_t)n);
-    if (e != cudaSuccess) { cudaFree(d_r); daisy_set_error("daisy_query_closest: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
+    cudaError_t e = dz_scratch(ctx, 0, sizeof(float) * 6 * (size_t)n, (void **)&d_r);
+    if (e == cudaSuccess) e = dz_scratch(ctx, 1, sizeof(daisy_hit) * (size_t)n, (void **)&d_h);
+    if (e != cudaSuccess) { daisy_set_error("daisy_query_closest: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
     int rc = DAISY_OK;
     e = cudaMemcpyAsync(d_r, rays6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) rc = dz_launch_closest(ctx, n, d_r, d_h);
     if (e == cudaSuccess && !rc) e = cudaMemcpyAsync(hits, d_h, sizeof(daisy_hit) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_r); cudaFree(d_h);
     if (e != cudaSuccess) { daisy_set_error("daisy_query_closest: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
     return rc;
 }

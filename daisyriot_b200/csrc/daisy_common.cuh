@@ -319,7 +319,12 @@ struct daisy_ctx {
     int64_t pairs_traced = 0, pairs_owned = 0, pairs_heavy = 0;
     double ff_ms = 0.0;
     int num_sms = 148;
+    // grow-only device buffers of the per-frame entry points (closest-hit queries, traceScreen): a frame loop does not pay a
+    // cudaMalloc / cudaFree pair per buffer per call (dz_scratch, api.cu)
+    void *scratch[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t scratch_bytes[6] = { 0, 0, 0, 0, 0, 0 };
 };
+cudaError_t dz_scratch(daisy_ctx *ctx, int slot, size_t bytes, void **out); // api.cu
 
 int dz_build_lbvh(daisy_ctx *ctx);                                   // bvh.cu
 int dz_launch_closest(daisy_ctx *ctx, int n, const float *d_rays, daisy_hit *d_hits); // bvh.cu

@@ -86,11 +86,11 @@ extern "C" int daisy_trace_screen(daisy_ctx *ctx, int width, int height, int sam
     const int N = ctx->N;
     float *d_rays = nullptr, *d_rgb = nullptr, *d_vcol = nullptr, *d_out = nullptr;
     daisy_hit *d_hits = nullptr;
-    cudaError_t e = cudaMalloc(&d_rays, sizeof(float) * 6 * nrays);
-    if (e == cudaSuccess) e = cudaMalloc(&d_rgb, sizeof(float) * 3 * (size_t)(N > 0 ? N : 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_vcol, sizeof(float) * 3 * (size_t)(ctx->nv > 0 ? ctx->nv : 1));
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(float) * 3 * (size_t)npix);
-    if (e == cudaSuccess && hits_out) e = cudaMalloc(&d_hits, sizeof(daisy_hit) * nrays);
+    cudaError_t e = dz_scratch(ctx, 0, sizeof(float) * 6 * nrays, (void **)&d_rays);
+    if (e == cudaSuccess) e = dz_scratch(ctx, 2, sizeof(float) * 3 * (size_t)(N > 0 ? N : 1), (void **)&d_rgb);
+    if (e == cudaSuccess) e = dz_scratch(ctx, 3, sizeof(float) * 3 * (size_t)(ctx->nv > 0 ? ctx->nv : 1), (void **)&d_vcol);
+    if (e == cudaSuccess) e = dz_scratch(ctx, 4, sizeof(float) * 3 * (size_t)npix, (void **)&d_out);
+    if (e == cudaSuccess && hits_out) e = dz_scratch(ctx, 1, sizeof(daisy_hit) * nrays, (void **)&d_hits);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays6, sizeof(float) * 6 * nrays, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess && N > 0) e = cudaMemcpyAsync(d_rgb, patch_rgb, sizeof(float) * 3 * (size_t)N, cudaMemcpyHostToDevice, st);
     f3 eye; eye.x = eye3[0]; eye.y = eye3[1]; eye.z = eye3[2];
@@ -103,7 +103,6 @@ extern "C" int daisy_trace_screen(daisy_ctx *ctx, int width, int height, int sam
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb, d_out, sizeof(float) * 3 * (size_t)npix, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && hits_out) e = cudaMemcpyAsync(hits_out, d_hits, sizeof(daisy_hit) * nrays, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_rays); cudaFree(d_rgb); cudaFree(d_vcol); cudaFree(d_out); cudaFree(d_hits);
     nvtxRangePop();
     if (e != cudaSuccess) { daisy_set_error("daisy_trace_screen: %s", cudaGetErrorString(e)); return DAISY_E_CUDA; }
     return DAISY_OK;
