@@ -419,6 +419,7 @@ __device__ __forceinline__ int shaft_candidates(const BvhNode *__restrict__ node
     fmask = 0;
     for (int f = 0; f < nfaces; f++) {
         if (f + 1 == skip_lo || f + 1 == skip_hi) continue;
+        DZ_ASSERT(f < DAISY_MAX_FACES);
         const float4 b0 = __ldg(&faces[f].blo), b1 = __ldg(&faces[f].bhi);
         if (shaft_box(sh, b0.x, b0.y, b0.z, b1.x, b1.y, b1.z)) fmask |= 1ull << f;
     }
@@ -485,6 +486,7 @@ struct FaceTables {
     const int *cells, *lists;
     const BvhNode *nodes;
     int root;
+    int64_t ncells, nlist; // table sizes (bounds checks of the checked build)
     float tm;  // margin on the ray parameter: crossings within tm of either end point are resolved by explicit tests
     float eps; // a ray can only touch a triangle of a face where it runs within eps of the face's plane
 };
@@ -604,10 +606,12 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                                         jb0 = max(ib0, (int)floorf(fminf(cb0, cb1) - 0.01f)); jb1 = min(ib1, (int)floorf(fmaxf(cb0, cb1) + 0.01f));
                                     }
                                     for (int ib = jb0; ib <= jb1 && alive; ib++) {
+                                        DZ_ASSERT(ia >= 0 && ia < g.x && ib >= 0 && ib < g.y && (int64_t)g.z + (int64_t)ib * g.x + ia < ft.ncells);
                                         const int c = __ldg(ft.cells + g.z + ib * g.x + ia);
                                         if (c < 0) continue;
                                         const int *L = ft.lists + (c >> 1);
                                         const int n = __ldg(L);
+                                        DZ_ASSERT((int64_t)(c >> 1) + n < ft.nlist && n > 0);
                                         for (int q = 1; q <= n; q++) {
                                             const int k = __ldg(L + q);
                                             if (k == lo || k == hi || k == prev1 || k == prev2) continue;
@@ -637,6 +641,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                     const float ca = fmaf(X, ex.x, fmaf(Y, ex.y, fmaf(Z, ex.z, ex.w)));
                     const float cb = fmaf(X, ey.x, fmaf(Y, ey.y, fmaf(Z, ey.z, ey.w)));
                     if (ca >= 0.f && cb >= 0.f && ca < (float)g.x && cb < (float)g.y) {
+                        DZ_ASSERT((int)ca >= 0 && (int)ca < g.x && (int)cb >= 0 && (int)cb < g.y && (int64_t)g.z + (int64_t)(int)cb * g.x + (int)ca < ft.ncells);
                         const int c = __ldg(ft.cells + g.z + (int)cb * g.x + (int)ca);
 #ifdef DAISY_FF_STATS
                         atomicAdd(&g_ffstats[15], 1ull);
@@ -651,7 +656,7 @@ __device__ __forceinline__ uint64_t pair_mask_warp(const TriVerts *__restrict__ 
                             else {
                                 const int *L = ft.lists + (c >> 1);
                                 const int n = __ldg(L);
-                                DZ_ASSERT(n > 0);
+                                DZ_ASSERT(n > 0 && (int64_t)(c >> 1) + n < ft.nlist);
                                 for (int q = 1; q <= n; q++) {
                                     const int k = __ldg(L + q);
                                     if (k == lo || k == hi) continue;
@@ -819,6 +824,7 @@ struct FFParams {
     const DzFace *faces;  // planar face grids (faces.cu): face f = plane id f + 1
     const int *face_cells, *face_lists;
     int nfaces;
+    int64_t face_ncells, face_nlist;
     float face_tm;
     const int *order;     // tile composition: slot -> triangle id (-1 = empty slot); tile T holds slots [64 T, 64 T + 64)
     int n_inner;          // samples [0, n_inner) of the device-order pattern are inner samples
@@ -1007,6 +1013,7 @@ __global__ void __launch_bounds__(FF_THREADS, FF_MINBLOCKS) k_ff_tiles(FFParams 
         };
         FaceTables ftab;
         ftab.faces = P.faces; ftab.cells = P.face_cells; ftab.lists = P.face_lists; ftab.tm = P.face_tm;
+        ftab.ncells = P.face_ncells; ftab.nlist = P.face_nlist;
         ftab.nodes = P.nodes; ftab.root = P.root; ftab.eps = 0.0625f * P.face_tm;
         while (true) { // 2a
             int q0 = 0;
@@ -1214,6 +1221,7 @@ int dz_build_formfactors(daisy_ctx *ctx, int variant, uint64_t *d_masks, int mro
     P.order = ctx->d_order;
     P.plane = ctx->d_plane; P.pid = ctx->d_pid; P.nbr = ctx->d_nbr; P.n_inner = ctx->n_nonedge;
     P.faces = ctx->d_faces; P.face_cells = ctx->d_face_cells; P.face_lists = ctx->d_face_lists; P.nfaces = ctx->nfaces; P.face_tm = 4.0f * ctx->pad;
+    P.face_ncells = ctx->face_cells; P.face_nlist = ctx->face_list_ints;
 
     { const char *e = getenv("DAISY_FF_RING"); P.ring_on = !(e && e[0] == '0'); }
     P.all_heavy = 0;
