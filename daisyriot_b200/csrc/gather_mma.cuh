@@ -164,6 +164,8 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
     if (warp == 0) {
         // ------------------------------- TMA producer -------------------------------
         if (lane == 0) {
+            uint64_t pol_first;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
                 const int rb = item / P.nsplit, split = item - rb * P.nsplit;
                 const int c_begin = split * P.colw, c_end = min(P.ncols, c_begin + P.colw);
@@ -175,8 +177,9 @@ k_gather_mma(GatherParams P, const __grid_constant__ CUtensorMap tmF, const __gr
                     unsigned char *sf = base + (size_t)st * STAGE;
                     const int c0 = c_begin + s * MM_COLS;
                     mbar_expect_tx(&full[st], (uint32_t)STAGE);
-                    tma_load_2d(sf, &tmF, c0, rb * MM_ROWS, &full[st]);
-                    tma_load_2d(sf + F_SUB, &tmF, c0 + MM_SUB, rb * MM_ROWS, &full[st]);
+                    // F streams through L2 evict_first: it is read once per pass and must not push the split residual out
+                    tma_load_2d_hint(sf, &tmF, c0, rb * MM_ROWS, &full[st], pol_first);
+                    tma_load_2d_hint(sf + F_SUB, &tmF, c0 + MM_SUB, rb * MM_ROWS, &full[st], pol_first);
                     tma_load_2d(sf + B_OFF, &tmR, c0, 0, &full[st]);
                     tma_load_2d(sf + B_OFF + B_SUB, &tmR, c0 + MM_SUB, 0, &full[st]);
                 }
