@@ -646,13 +646,18 @@ def run_ours(args):
             mid = (np.float32(0.5) * (lo + hi)).astype(np.float32)
             cam.dir = mid.copy()
             cam.eye = np.array([mid[0], mid[1], hi[2] + np.float32(1.6) * (hi[2] - lo[2])], np.float32)
-            cam_rays = np.ascontiguousarray(cam.gen_rays_for_screen(True), np.float32)
-            nr = cam_rays.reshape(-1, 6).shape[0]
-            hits = optixP.optixQuery(nr, cam_rays)
+            gen = np.ascontiguousarray(cam.gen_rays_for_screen(True), np.float32)
+            nr = gen.reshape(-1, 6).shape[0]
+            # pinned host buffers on both sides, as for the gather's host-buffer steps
+            from daisyriot_b200.api import HIT_DTYPE
+            cam_rays = torch.empty(gen.size, dtype=torch.float32, pin_memory=True).numpy()
+            cam_rays[:] = gen.reshape(-1)
+            hits = torch.empty(nr * HIT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True).numpy().view(HIT_DTYPE)
+            optixP.optixQuery(nr, cam_rays, hits)
             ts = []
             for _ in range(3):
                 t0 = time.time(); optixP.optixQuery(nr, cam_rays, hits); ts.append(time.time() - t0)
-            closest = {"metric": "closest_hit_rays_per_s through host buffers (daisy_query_closest: H2D 24 B/ray, D2H 16 B/ray)", "rays": int(nr),
+            closest = {"metric": "closest_hit_rays_per_s through pinned host buffers (daisy_query_closest: H2D 24 B/ray, D2H 16 B/ray)", "rays": int(nr),
                        "value": nr / min(ts), "seconds": min(ts), "hit_fraction": float((hits["t"] > 0).mean())}
         except Exception as ex:
             closest = {"failed": repr(ex)}

@@ -263,6 +263,34 @@ def test_face_grids_host_side(fixture_scenes):
     st2, _ = grids(sc2)
     f0 = int(np.argmin(st2[:, 0]))                                   # the face that lost 32 triangles
     assert st2[f0, 0] == 512 - 32 and st2[f0, 4] > st[0, 4] and st2[f0, 2] > st[0, 2]
+    # T-junctions: one 8 x 8 sheet with a cell cut in four next to uncut neighbours.  The halves of the uncut neighbours' edges are
+    # not shared by exactly two triangles, so the cells along them turn mixed although the sheet has no hole
+    def sheet(split):
+        V, T = [], []
+
+        def vid(x, z):
+            V.append((x, 0.0, z))
+            return len(V) - 1
+
+        g = [[vid(i, j) for i in range(9)] for j in range(9)]
+        for j in range(8):
+            for i in range(8):
+                a, b, c, d = g[j][i], g[j][i + 1], g[j + 1][i], g[j + 1][i + 1]
+                if split and (i, j) == (3, 4):
+                    m = [[a, vid(i + .5, j), b], [vid(i, j + .5), vid(i + .5, j + .5), vid(i + 1, j + .5)], [c, vid(i + .5, j + 1), d]]
+                    for jj in range(2):
+                        for ii in range(2):
+                            q = (m[jj][ii], m[jj][ii + 1], m[jj + 1][ii], m[jj + 1][ii + 1])
+                            T += [[q[0], q[3], q[1], 0, 0, 0], [q[0], q[2], q[3], 0, 0, 0]]
+                else:
+                    T += [[a, d, b, 0, 0, 0], [a, c, d, 0, 0, 0]]
+        return scenes.Scene(np.asarray(V, np.float32), np.array([[0, 1, 0]], np.float32), np.asarray(T, np.int32),
+                            np.zeros(len(T), np.int32), sc.materials, "sheet")
+
+    plain, cut = grids(sheet(False))[0], grids(sheet(True))[0]
+    assert plain.shape[0] == 1 and cut.shape[0] == 1 and cut[0, 0] == plain[0, 0] + 6
+    # (six more, smaller triangles: the cell size differs a little, so fractions are compared) a larger share of mixed cells
+    assert cut[0, 4] / cut[0, 1] > 1.03 * plain[0, 4] / plain[0, 1]
     # curved geometry has no faces to speak of; the box around the balls does
     stc, _ = grids(fixture_scenes["colorballs"])
     assert 1 <= stc.shape[0] <= 64
