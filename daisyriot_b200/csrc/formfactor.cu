@@ -18,9 +18,15 @@
 
 #define TILE 64
 #define NBR_CAP 32 // ints per triangle in the neighbour table: [0] = count, then up to 31 triangles of its own plane
-#define FF_THREADS 256
+// CTA shape: 512 threads x 2 CTAs per SM = the same 32 warps per SM at 64 registers as 256 x 4, but half the shared memory
+// (two tiles in flight per SM instead of four), which leaves the SM ~124 KB of L1 instead of ~28 KB for the face tables, cell
+// lists, vertices and neighbour lists the rays gather from: 537 -> 506 ms at 32K patches, 73 -> 63 / 58 -> 47 ms on the
+// reference's scenes (384 x 3: 518 ms; 1024 x 1: 595 ms, the tile barriers bite).
+#ifndef FF_THREADS
+#define FF_THREADS 512
+#endif
 #ifndef FF_MINBLOCKS
-#define FF_MINBLOCKS 4
+#define FF_MINBLOCKS 2
 #endif
 #define PI_D 3.14159265358979323846
 #define PI_F 3.14159265358979323846f
