@@ -146,7 +146,9 @@ static void build_one_face(double ext, float pad, const float *vertices, const i
     }
     if (!(best < 1e300)) return;
     // cell size: FACE_CELLS_PER_TRI cells per average triangle, never below 2 delta, grid bounded
-    double cs = sqrt(area_sum / ((double)mem.size() * FACE_CELLS_PER_TRI));
+    double cells_per_tri = FACE_CELLS_PER_TRI;
+    { const char *e = getenv("DAISY_FACE_CELLS_PER_TRI"); if (e && atof(e) >= 1.0) cells_per_tri = atof(e); } // A/B switch
+    double cs = sqrt(area_sum / ((double)mem.size() * cells_per_tri));
     cs = fmax(cs, 2.0 * delta);
     int nx = 0, ny = 0;
     for (int it = 0; it < 64; it++) {
