@@ -43,6 +43,7 @@ SYMBOLS = {
     "daisy_ctx_set_stream": (_i, [_vp, _vp]),
     "daisy_plane_ids": (_i, [_fp, _i, _ip, _i, _ip]),
     "daisy_ctx_face_count": (_i, [_vp]),
+    "daisy_face_grid_dump": (_i, [_fp, _i, _ip, _i, _i, _fp, C.POINTER(C.c_int8), _ip, C.c_int64]),
     "daisy_face_grid_stats": (_i, [_fp, _i, _ip, _i, _i, _i64p, _ip, _ip]),
     "daisy_query_closest": (_i, [_vp, _i, _fp, _vp]),
     "daisy_query_closest_device": (_i, [_vp, _i, _vp, _vp]),

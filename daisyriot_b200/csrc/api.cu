@@ -253,6 +253,25 @@ extern "C" int daisy_face_grid_stats(const float *vertices, int nv, const int32_
     return DAISY_OK;
 }
 
+int dz_face_grid_dump(float ext, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid, int face, float *frame16, signed char *state,
+                      int32_t *count, int64_t cap); // faces.cu
+extern "C" int daisy_face_grid_dump(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int face, float *frame16, signed char *state, int32_t *count,
+                                    int64_t capacity) {
+    DZ_REQUIRE(ntri > 0 && nv > 0 && vertices && tri_idx && frame16, DAISY_E_INVALID, "daisy_face_grid_dump: bad argument");
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int i = 0; i < ntri; i++)
+        for (int k = 0; k < 3; k++) {
+            const int v = tri_idx[6 * (size_t)i + k];
+            DZ_REQUIRE(v >= 0 && v < nv, DAISY_E_INVALID, "daisy_face_grid_dump: triangle index out of range");
+            for (int d = 0; d < 3; d++) { lo[d] = fminf(lo[d], vertices[3 * (size_t)v + d]); hi[d] = fmaxf(hi[d], vertices[3 * (size_t)v + d]); }
+        }
+    float ext = 0.f;
+    for (int d = 0; d < 3; d++) ext = fmaxf(ext, hi[d] - lo[d]);
+    std::vector<int> pid;
+    assign_plane_ids(vertices, tri_idx, ntri, ext, pid);
+    return dz_face_grid_dump(ext, vertices, tri_idx, ntri, pid, face, frame16, state, count, capacity);
+}
+
 static void set_partition(daisy_ctx *c, int rank, int nranks) {
     c->rank = rank; c->nranks = nranks;
     int n = (c->N + nranks - 1) / nranks;

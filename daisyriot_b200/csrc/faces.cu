@@ -365,3 +365,25 @@ int dz_face_grid_stats(float ext, const float *vertices, const int32_t *tri_idx,
     }
     return DAISY_OK;
 }
+
+// Host-only dump of one face's grid for the CPU property tests: frame16 = plane (n, d), ex (xyz / cell size, offset), ey, nx, ny,
+// triangle count, 0; state[q] = 0 empty / 1 covered / 2 mixed, count[q] = listed triangles (both nx * ny long, may be NULL).
+int dz_face_grid_dump(float ext, const float *vertices, const int32_t *tri_idx, int ntri, std::vector<int> &pid, int face, float *frame16, signed char *state,
+                      int32_t *count, int64_t cap) {
+    std::vector<DzFace> faces;
+    std::vector<int> cells, lists;
+    const int rc = build_face_tables(ext, 1e-4f * ext, vertices, tri_idx, ntri, pid, faces, cells, lists);
+    if (rc) return rc;
+    if (face < 0 || face >= (int)faces.size()) { daisy_set_error("daisy_face_grid_dump: no such face"); return DAISY_E_INVALID; }
+    const DzFace &F = faces[(size_t)face];
+    const float fr[16] = { F.pl.x, F.pl.y, F.pl.z, F.pl.w, F.ex.x, F.ex.y, F.ex.z, F.ex.w, F.ey.x, F.ey.y, F.ey.z, F.ey.w, (float)F.g.x, (float)F.g.y, (float)F.g.w, 0.f };
+    memcpy(frame16, fr, sizeof(fr));
+    const int64_t n = (int64_t)F.g.x * F.g.y;
+    if ((state || count) && cap < n) { daisy_set_error("daisy_face_grid_dump: buffers too small"); return DAISY_E_INVALID; }
+    for (int64_t q = 0; q < n && (state || count); q++) {
+        const int c = cells[(size_t)F.g.z + (size_t)q];
+        if (state) state[q] = c < 0 ? 0 : ((c & 1) ? 1 : 2);
+        if (count) count[q] = c < 0 ? 0 : lists[(size_t)(c >> 1)];
+    }
+    return DAISY_OK;
+}

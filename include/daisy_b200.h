@@ -65,6 +65,11 @@ int daisy_plane_ids(const float *vertices, int nv, const int32_t *tri_idx, int n
  * form-factor kernel resolves a visibility ray against a whole face with one plane crossing and one cell lookup.
  * stats6[6 f ..] = triangles, cells, empty, covered, mixed cells, list entries of face f (f < max_faces); pid_out (may be
  * NULL) = the plane ids after renumbering (face f = id f + 1). */
+/* diagnostic, host only: one face's grid -- frame16 = plane (n, d), in-plane axes scaled to cell units with their offsets (cell
+ * coordinate a = dot(X, ex.xyz) + ex.w, b likewise), nx, ny, triangle count, 0; state[q] (q = b * nx + a, `capacity` entries) =
+ * 0 empty / 1 covered / 2 mixed, count[q] = triangles listed for the cell.  state / count may be NULL (frame only). */
+int daisy_face_grid_dump(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int face, float *frame16, signed char *state, int32_t *count,
+                         int64_t capacity);
 int daisy_face_grid_stats(const float *vertices, int nv, const int32_t *tri_idx, int ntri, int max_faces, int64_t *stats6, int32_t *nfaces_out, int32_t *pid_out);
 /* multi-GPU (one process per GPU): this context builds and owns the row block `rank` of `nranks` equal blocks of
  * rows_per_rank = ceil(N/nranks) rounded up to a multiple of 256 when nranks > 1 (a 256-column TMA tile of the

@@ -296,6 +296,111 @@ def test_face_grids_host_side(fixture_scenes):
     assert 1 <= stc.shape[0] <= 64
 
 
+def test_face_grid_cells_mean_what_they_say():
+    """The two claims the form-factor kernel builds on (csrc/faces.cu), checked on the CPU against plain geometry for a ragged,
+    perforated, T-junctioned, arbitrarily rotated sheet: every point of a COVERED cell (grown by delta) lies in some triangle of
+    the face, and no triangle of the face comes within delta of an EMPTY cell.  The cell lists must name every triangle that
+    touches the grown cell."""
+    import ctypes as C
+    from daisyriot_b200 import scenes
+    L = _lib.lib()
+    rng = np.random.RandomState(7)
+    V, T = [], []
+
+    def vid(s, t):
+        V.append((s, t))
+        return len(V) - 1
+
+    nu = nv = 10
+    holes = rng.uniform(size=(nv, nu)) < 0.2
+    splits = rng.uniform(size=(nv, nu)) < 0.2
+    g = [[vid(i / nu, j / nv) for i in range(nu + 1)] for j in range(nv + 1)]
+    for j in range(nv):
+        for i in range(nu):
+            if holes[j, i] or (i > 6 and j > 7):
+                continue
+            a, b, c, d = g[j][i], g[j][i + 1], g[j + 1][i], g[j + 1][i + 1]
+            quads = [(a, b, c, d)]
+            if splits[j, i]:
+                m = [[a, vid((i + .5) / nu, j / nv), b], [vid(i / nu, (j + .5) / nv), vid((i + .5) / nu, (j + .5) / nv), vid((i + 1) / nu, (j + .5) / nv)],
+                     [c, vid((i + .5) / nu, (j + 1) / nv), d]]
+                quads = [(m[jj][ii], m[jj][ii + 1], m[jj + 1][ii], m[jj + 1][ii + 1]) for jj in range(2) for ii in range(2)]
+            for q in quads:
+                T += [[q[0], q[1], q[3], 0, 0, 0], [q[0], q[3], q[2], 0, 0, 0]] if rng.uniform() < 0.5 else [[q[0], q[1], q[2], 0, 0, 0], [q[1], q[3], q[2], 0, 0, 0]]
+    st2 = np.asarray(V, np.float64)
+    # place the sheet in space: origin + s * eu + t * ev, rotated arbitrarily
+    ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(1.1) * K + (1 - np.cos(1.1)) * K @ K
+    P3 = (np.array([0.3, 1.0, -0.4]) + st2[:, :1] * np.array([4.0, 0, 0]) + st2[:, 1:] * np.array([0, 0.2, 3.0])) @ R.T
+    v = np.ascontiguousarray(P3, np.float32)
+    t = np.ascontiguousarray(T, np.int32)
+    assert len(t) >= 32
+    frame = np.zeros(16, np.float32)
+    _lib.check(L.daisy_face_grid_dump(_lib.fptr(v), v.shape[0], _lib.iptr(t), t.shape[0], 0, _lib.fptr(frame), None, None, 0))
+    nx, ny, ntri = int(frame[12]), int(frame[13]), int(frame[14])
+    assert ntri == len(t)
+    state = np.zeros(nx * ny, np.int8)
+    count = np.zeros(nx * ny, np.int32)
+    _lib.check(L.daisy_face_grid_dump(_lib.fptr(v), v.shape[0], _lib.iptr(t), t.shape[0], 0, _lib.fptr(frame), state.ctypes.data_as(C.POINTER(C.c_int8)),
+                                      _lib.iptr(count), nx * ny))
+    state, count = state.reshape(ny, nx), count.reshape(ny, nx)
+    assert (state == 1).sum() > 200 and (state == 2).sum() > 50 and (state == 0).sum() > 20
+    # triangles in cell coordinates (a, b)
+    vd = v.astype(np.float64)
+    ex, ey = frame[4:8].astype(np.float64), frame[8:12].astype(np.float64)
+    ab = np.stack([vd @ ex[:3] + ex[3], vd @ ey[:3] + ey[3]], 1)
+    tri = ab[t[:, :3]]                                                   # (ntri, 3, 2)
+    cs = 1.0 / np.linalg.norm(ex[:3])                                    # world units per cell
+    used = np.unique(t[:, :3])                                           # the scene extent runs over the vertices the triangles use
+    ext = float((v[used].max(0) - v[used].min(0)).max())
+    dl = 0.999 * 2.5e-4 * ext / cs                                       # delta in cell units (a hair inside: the frame is float32)
+
+    def inside_any(p, tol):
+        d0 = tri[:, 1] - tri[:, 0]; d1 = tri[:, 2] - tri[:, 1]; d2 = tri[:, 0] - tri[:, 2]
+        c0 = d0[:, 0] * (p[1] - tri[:, 0, 1]) - d0[:, 1] * (p[0] - tri[:, 0, 0])
+        c1 = d1[:, 0] * (p[1] - tri[:, 1, 1]) - d1[:, 1] * (p[0] - tri[:, 1, 0])
+        c2 = d2[:, 0] * (p[1] - tri[:, 2, 1]) - d2[:, 1] * (p[0] - tri[:, 2, 0])
+        sgn = np.sign(d0[:, 0] * (tri[:, 2, 1] - tri[:, 0, 1]) - d0[:, 1] * (tri[:, 2, 0] - tri[:, 0, 0]))
+        return ((c0 * sgn >= -tol) & (c1 * sgn >= -tol) & (c2 * sgn >= -tol)).any()
+
+    def seg_dist(p, a, b):
+        ab_, ap = b - a, p - a
+        s_ = np.clip((ap * ab_).sum(-1) / np.maximum((ab_ * ab_).sum(-1), 1e-300), 0, 1)
+        return np.linalg.norm(ap - s_[:, None] * ab_, axis=-1)
+
+    def dist_to_faces(p):
+        if inside_any(p, 0.0):
+            return 0.0
+        return min(seg_dist(p, tri[:, k], tri[:, (k + 1) % 3]).min() for k in range(3))
+
+    checked = [0, 0]
+    for j in range(ny):
+        for i in range(nx):
+            pts = [(i + fx, j + fy) for fx in (-dl, 0.5, 1 + dl) for fy in (-dl, 0.5, 1 + dl)]   # corners of the grown cell, mid points, centre
+            if state[j, i] == 1:
+                assert all(inside_any(np.array(p), 1e-9) for p in pts), ("covered cell leaves the face", i, j)
+                checked[0] += 1
+            elif state[j, i] == 0:
+                assert min(dist_to_faces(np.array(p)) for p in pts) > 0.0 and dist_to_faces(np.array((i + .5, j + .5))) > dl, ("triangle near an empty cell", i, j)
+                assert count[j, i] == 0
+                checked[1] += 1
+            if state[j, i] != 0:
+                # the list names every triangle that overlaps the cell (at least those containing one of the sample points)
+                touching = set()
+                for p in pts:
+                    p = np.array(p)
+                    d0 = tri[:, 1] - tri[:, 0]
+                    sgn = np.sign(d0[:, 0] * (tri[:, 2, 1] - tri[:, 0, 1]) - d0[:, 1] * (tri[:, 2, 0] - tri[:, 0, 0]))
+                    ok = np.ones(len(tri), bool)
+                    for k in range(3):
+                        dk = tri[:, (k + 1) % 3] - tri[:, k]
+                        ok &= (dk[:, 0] * (p[1] - tri[:, k, 1]) - dk[:, 1] * (p[0] - tri[:, k, 0])) * sgn >= 0
+                    touching |= set(np.nonzero(ok)[0].tolist())
+                assert count[j, i] >= len(touching), ("cell list too short", i, j, count[j, i], len(touching))
+    assert checked[0] > 200 and checked[1] > 20
+
+
 def test_committed_row_digests_cover_the_bench_workloads():
     import bench
     for name, (N, K, _) in bench.WORKLOADS.items():
